@@ -1,0 +1,90 @@
+"""Builds ``exahype_b200/libexahype_cuda.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m exahype_b200.build [--force] [--verbose]
+
+One translation unit per physics family, compiled in parallel; ``-fmad=false`` keeps the arithmetic of
+``physics.cuh`` contraction-free (bit-exactness against the reference, see csrc/physics.cuh); ``-lineinfo`` so
+that ncu's source page maps to these files.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libexahype_cuda.so")
+
+SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu"]
+HEADERS = ["fv_patch_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-lineinfo",
+              "-gencode", "arch=compute_100a,code=sm_100a",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def nvcc() -> str:
+    path = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(path):
+        raise RuntimeError("nvcc not found: libexahype_cuda.so cannot be built (there is no CPU fallback)")
+    return path
+
+
+def _host_compiler_args():
+    # the image's $CXX (/opt/gcc) works for nvcc; prefer the system g++ when present for a predictable ABI
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    headers = [os.path.join(CSRC, h) for h in HEADERS]
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc()] + NVCC_FLAGS + _host_compiler_args() + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(4, max(1, len(jobs)))) as pool:
+        for log in pool.map(compile_one, jobs):
+            if verbose and log:
+                print(log)
+
+    objs = [os.path.join(BUILD, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc(), "-shared", "-o", LIB] + objs + _host_compiler_args() + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))

@@ -1,0 +1,394 @@
+// libexahype_cuda.so -- C ABI (include/exahype_cuda.h) over the sm_100a kernel instantiations.
+//
+// Replaces, for a whole batch of patches and on the GPU, the reference's generated
+//   void time_step(double* Q, double dt)            ("Unit test/test.h":3, "Unit test/test.cpp":3-111)
+// There is deliberately no CPU implementation behind these entry points.
+#include "../../include/exahype_cuda.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fv_registry.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+  return fail(EXAHYPE_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+const std::vector<exahype::FvEntry>& registry() {
+  static const std::vector<exahype::FvEntry> all = [] {
+    std::vector<exahype::FvEntry> v;
+    for (exahype::FvEntryList l : {exahype::euler3d_entries(), exahype::euler2d_entries(), exahype::swe2d_entries()})
+      v.insert(v.end(), l.entries, l.entries + l.count);
+    return v;
+  }();
+  return all;
+}
+
+// mirrors KernelBuilder.viable() (reference exahype/KernelBuilder.py:41-48) plus what the stencil needs
+int validate(const exahype_fv_config* cfg) {
+  if (!cfg) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cfg is null");
+  if (cfg->dim != 2 && cfg->dim != 3) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "check viability of inputs: dim must be 2 or 3 (got %d)", cfg->dim);
+  if (cfg->patch_size < 1) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "check viability of inputs: patch_size must be >= 1 (got %d)", cfg->patch_size);
+  if (cfg->halo < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "check viability of inputs: halo_size must be >= 0 (got %d)", cfg->halo);
+  if (cfg->halo < 1) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "the Rusanov update reads one halo layer: halo_size must be >= 1");
+  if (cfg->n_real < 1 || cfg->n_aux < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_real must be >= 1 and n_aux >= 0");
+  if (cfg->dtype != EXAHYPE_DTYPE_F64 && cfg->dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
+  if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
+  if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown flag bits 0x%x", cfg->flags);
+  return EXAHYPE_OK;
+}
+
+const exahype::FvEntry* find(const exahype_fv_config* cfg) {
+  for (const exahype::FvEntry& e : registry()) {
+    const exahype_fv_config& c = e.cfg;
+    if (c.model == cfg->model && c.dtype == cfg->dtype && c.dim == cfg->dim && c.patch_size == cfg->patch_size &&
+        c.halo == cfg->halo && c.n_real == cfg->n_real && c.n_aux == cfg->n_aux)
+      return &e;
+  }
+  return nullptr;
+}
+
+int variant_of(unsigned flags) {
+  return ((flags & EXAHYPE_FLAG_DISSIPATION_ALL) ? 1 : 0) | ((flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) ? 2 : 0);
+}
+
+size_t elem_size(int dtype) { return dtype == EXAHYPE_DTYPE_F64 ? 8 : 4; }
+
+long long ipow_ll(long long b, int e) {
+  long long r = 1;
+  while (e-- > 0) r *= b;
+  return r;
+}
+
+int lookup(const exahype_fv_config* cfg, const exahype::FvEntry** entry) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  *entry = find(cfg);
+  if (!*entry)
+    return fail(EXAHYPE_ERR_NO_INSTANTIATION,
+                "no committed instantiation for model=%d dtype=%d dim=%d patch_size=%d halo=%d n_real=%d n_aux=%d; "
+                "generate one with exahype.printers.CUDAPrinter",
+                cfg->model, cfg->dtype, cfg->dim, cfg->patch_size, cfg->halo, cfg->n_real, cfg->n_aux);
+  return EXAHYPE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int exahype_cuda_version(void) { return EXAHYPE_CUDA_ABI_VERSION; }
+
+const char* exahype_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int exahype_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int exahype_cuda_fv_supported(const exahype_fv_config* cfg) { return (cfg && find(cfg)) ? 1 : 0; }
+
+int exahype_cuda_fv_list(exahype_fv_config* out, int capacity) {
+  const auto& r = registry();
+  for (int i = 0; i < (int)r.size() && i < capacity && out; ++i) out[i] = r[i].cfg;
+  return (int)r.size();
+}
+
+int64_t exahype_cuda_launch_count(void) { return g_launches.load(); }
+
+int exahype_cuda_fv_launch_info(const exahype_fv_config* cfg, int64_t n_patches, int* grid, int* block,
+                                int* smem_bytes, int* patches_per_tile) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  exahype::FvLaunchInfo info;
+  cudaError_t err = e->prepare[variant_of(cfg->flags)](&info, n_patches);
+  if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_launch_info");
+  if (grid) *grid = info.grid;
+  if (block) *block = info.block;
+  if (smem_bytes) *smem_bytes = info.smem_bytes;
+  if (patches_per_tile) *patches_per_tile = info.patches_per_tile;
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q_out, int64_t n_patches, double dt,
+                         void* lambda_patch, void* lambda_max, void* stream) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  if (n_patches < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_patches must be >= 0 (got %lld)", (long long)n_patches);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (lambda_max && !(cfg->flags & EXAHYPE_FLAG_LAMBDA_ACCUMULATE)) {
+    cudaError_t err = cudaMemsetAsync(lambda_max, 0, elem_size(cfg->dtype), s);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaMemsetAsync(lambda_max)");
+  }
+  if (n_patches == 0) return EXAHYPE_OK;
+  if (!q_in || !q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must not be null");
+  if ((reinterpret_cast<uintptr_t>(q_in) & 15) || (reinterpret_cast<uintptr_t>(q_out) & 15))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must be 16-byte aligned (TMA bulk copies)");
+  if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
+  cudaError_t err = e->launch[variant_of(cfg->flags)](q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);
+  if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch");
+  g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
+
+#define EXAHYPE_NAMED_ENTRY(NAME, MODEL, DTYPE, DIM, NR, T)                                                     \
+  int NAME(const T* q_in, T* q_out, int64_t n_patches, int patch_size, int halo, int n_aux, T dt,               \
+           T* lambda_patch, T* lambda_max, unsigned flags, void* stream) {                                      \
+    exahype_fv_config cfg = {MODEL, DTYPE, DIM, patch_size, halo, NR, n_aux, flags};                            \
+    return exahype_cuda_fv_step(&cfg, q_in, q_out, n_patches, (double)dt, lambda_patch, lambda_max, stream);    \
+  }
+EXAHYPE_NAMED_ENTRY(exahype_cuda_fv_step_euler_2d_f64, EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, 2, 4, double)
+EXAHYPE_NAMED_ENTRY(exahype_cuda_fv_step_euler_3d_f64, EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, 3, 5, double)
+EXAHYPE_NAMED_ENTRY(exahype_cuda_fv_step_swe_2d_f64, EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, 2, 3, double)
+EXAHYPE_NAMED_ENTRY(exahype_cuda_fv_step_swe_2d_f32, EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, 2, 3, float)
+
+// ------------------------------------------------------------------------------------------------
+// time_step on HOST memory: chunked H2D -> kernel -> D2H pipeline over `depth` stream slots
+namespace {
+
+struct HostPipeline {
+  int device = -1;
+  int depth = 0;
+  size_t in_capacity = 0, out_capacity = 0, lam_capacity = 0;
+  std::vector<cudaStream_t> streams;
+  std::vector<void*> d_in, d_out, d_lam;
+  void* d_lam_max = nullptr;
+  void release() {
+    for (void* p : d_in) cudaFree(p);
+    for (void* p : d_out) cudaFree(p);
+    for (void* p : d_lam) cudaFree(p);
+    for (cudaStream_t s : streams) cudaStreamDestroy(s);
+    if (d_lam_max) cudaFree(d_lam_max);
+    d_in.clear(); d_out.clear(); d_lam.clear(); streams.clear();
+    d_lam_max = nullptr; depth = 0; in_capacity = out_capacity = lam_capacity = 0; device = -1;
+  }
+};
+
+std::mutex g_pipe_mutex;
+HostPipeline g_pipe;
+long long g_chunk_patches = 0;   // 0: derive from a ~32 MiB input chunk
+int g_depth = 3;
+
+}  // namespace
+
+int exahype_cuda_host_pipeline_configure(int64_t chunk_patches, int depth) {
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  if (chunk_patches < 0 || depth < 0 || depth > 8) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "bad pipeline configuration");
+  g_chunk_patches = chunk_patches;
+  if (depth > 0) g_depth = depth;
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_host_pipeline_release(void) {
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  g_pipe.release();
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_time_step_host(const exahype_fv_config* cfg, const void* q_host, void* q_out_host, int64_t n_patches,
+                                double dt, void* lambda_patch_host, void* lambda_max_host) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  if (n_patches < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_patches must be >= 0");
+  if (n_patches > 0 && (!q_host || !q_out_host)) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "host buffers must not be null");
+  const bool unhaloed = cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED;
+  if (unhaloed && q_host == q_out_host) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
+
+  const size_t es = elem_size(cfg->dtype);
+  const int nv = cfg->n_real + cfg->n_aux;
+  const size_t in_patch = (size_t)ipow_ll(cfg->patch_size + 2 * cfg->halo, cfg->dim) * nv * es;
+  const size_t out_patch = unhaloed ? (size_t)ipow_ll(cfg->patch_size, cfg->dim) * nv * es : in_patch;
+
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
+  long long chunk = g_chunk_patches > 0 ? g_chunk_patches : std::max<long long>(1, (long long)((32u << 20) / in_patch));
+  chunk = std::min<long long>(chunk, std::max<long long>(n_patches, 1));
+  const int depth = g_depth;
+  HostPipeline& p = g_pipe;
+  if (p.device != dev || p.depth != depth || p.in_capacity < (size_t)chunk * in_patch ||
+      p.out_capacity < (size_t)chunk * out_patch || p.lam_capacity < (size_t)chunk * es) {
+    p.release();
+    p.device = dev; p.depth = depth;
+    p.in_capacity = (size_t)chunk * in_patch;
+    p.out_capacity = (size_t)chunk * std::max(in_patch, out_patch);
+    p.lam_capacity = (size_t)chunk * es;
+    for (int i = 0; i < depth; ++i) {
+      cudaStream_t s; void *a = nullptr, *b = nullptr, *c = nullptr;
+      if ((err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { p.release(); return cuda_fail(err, "cudaStreamCreate"); }
+      p.streams.push_back(s);
+      if ((err = cudaMalloc(&a, p.in_capacity)) != cudaSuccess) { p.release(); return cuda_fail(err, "cudaMalloc(staging in)"); }
+      p.d_in.push_back(a);
+      if ((err = cudaMalloc(&b, p.out_capacity)) != cudaSuccess) { p.release(); return cuda_fail(err, "cudaMalloc(staging out)"); }
+      p.d_out.push_back(b);
+      if ((err = cudaMalloc(&c, p.lam_capacity)) != cudaSuccess) { p.release(); return cuda_fail(err, "cudaMalloc(lambda)"); }
+      p.d_lam.push_back(c);
+    }
+    if ((err = cudaMalloc(&p.d_lam_max, 8)) != cudaSuccess) { p.release(); return cuda_fail(err, "cudaMalloc(lambda_max)"); }
+  }
+
+  if ((err = cudaMemsetAsync(p.d_lam_max, 0, 8, p.streams[0])) != cudaSuccess) return cuda_fail(err, "cudaMemsetAsync");
+  if ((err = cudaStreamSynchronize(p.streams[0])) != cudaSuccess) return cuda_fail(err, "cudaStreamSynchronize");
+
+  exahype_fv_config dev_cfg = *cfg;
+  dev_cfg.flags |= EXAHYPE_FLAG_LAMBDA_ACCUMULATE;
+  const char* src = static_cast<const char*>(q_host);
+  char* dst = static_cast<char*>(q_out_host);
+  long long slot_idx = 0;
+  for (long long first = 0; first < n_patches; first += chunk, ++slot_idx) {
+    const long long n = std::min<long long>(chunk, n_patches - first);
+    const int k = (int)(slot_idx % depth);
+    cudaStream_t s = p.streams[k];
+    // stream order makes reuse of slot k safe: its previous D2H is ahead of this H2D on the same stream
+    if ((err = cudaMemcpyAsync(p.d_in[k], src + (size_t)first * in_patch, (size_t)n * in_patch, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+      return cuda_fail(err, "cudaMemcpyAsync(H2D)");
+    // haloed output: update in place in the staging buffer and copy whole patches back (halos are unchanged)
+    void* d_out = unhaloed ? p.d_out[k] : p.d_in[k];
+    rc = exahype_cuda_fv_step(&dev_cfg, p.d_in[k], d_out, n, dt, lambda_patch_host ? p.d_lam[k] : nullptr,
+                              p.d_lam_max, s);
+    if (rc) return rc;
+    if ((err = cudaMemcpyAsync(dst + (size_t)first * out_patch, d_out, (size_t)n * out_patch, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+      return cuda_fail(err, "cudaMemcpyAsync(D2H)");
+    if (lambda_patch_host &&
+        (err = cudaMemcpyAsync(static_cast<char*>(lambda_patch_host) + (size_t)first * es, p.d_lam[k], (size_t)n * es,
+                               cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+      return cuda_fail(err, "cudaMemcpyAsync(lambda D2H)");
+  }
+  for (cudaStream_t s : p.streams)
+    if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(err, "cudaStreamSynchronize");
+  if (lambda_max_host) {
+    if ((err = cudaMemcpy(lambda_max_host, p.d_lam_max, es, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      return cuda_fail(err, "cudaMemcpy(lambda_max)");
+  }
+  return EXAHYPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL all-reduce(max) of the admissible-time-step scalar.  libnccl is loaded lazily so the library itself has no
+// link-time dependency on it (CPU-only hosts can still load libexahype_cuda.so and list its symbols).
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclFloat32_ = 7, ncclFloat64_ = 8 };   // nccl.h: ncclFloat = 7, ncclDouble = 8
+enum { ncclMax_ = 2 };                         // nccl.h: ncclSum 0, ncclProd 1, ncclMax 2, ncclMin 3
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string why;
+};
+
+NcclApi& nccl() {
+  static NcclApi api = [] {
+    NcclApi a;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (a.handle) break;
+    }
+    if (!a.handle) {
+      a.why = std::string("cannot load libnccl: ") + dlerror();
+      return a;
+    }
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.handle, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.handle, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.handle, "ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.handle, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString) {
+      a.why = "libnccl is missing a required symbol";
+      a.handle = nullptr;
+    }
+    return a;
+  }();
+  return api;
+}
+
+int nccl_fail(int code, const char* what) {
+  return fail(EXAHYPE_ERR_NCCL, "%s: %s", what, nccl().GetErrorString ? nccl().GetErrorString(code) : "?");
+}
+
+}  // namespace
+
+int exahype_cuda_nccl_unique_id(void* id128) {
+  if (!id128) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "id128 is null");
+  if (!nccl().handle) return fail(EXAHYPE_ERR_UNAVAILABLE, "%s", nccl().why.c_str());
+  ncclUniqueId id;
+  int rc = nccl().GetUniqueId(&id);
+  if (rc != ncclSuccess_) return nccl_fail(rc, "ncclGetUniqueId");
+  std::memcpy(id128, &id, sizeof id);
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_comm_init(void** comm, const void* id128, int world_size, int rank) {
+  if (!comm || !id128 || world_size < 1 || rank < 0 || rank >= world_size)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "bad communicator arguments (world_size=%d rank=%d)", world_size, rank);
+  if (!nccl().handle) return fail(EXAHYPE_ERR_UNAVAILABLE, "%s", nccl().why.c_str());
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  ncclComm_t c = nullptr;
+  int rc = nccl().CommInitRank(&c, world_size, id, rank);
+  if (rc != ncclSuccess_) return nccl_fail(rc, "ncclCommInitRank");
+  *comm = c;
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_comm_destroy(void* comm) {
+  if (!comm) return EXAHYPE_OK;
+  if (!nccl().handle) return fail(EXAHYPE_ERR_UNAVAILABLE, "%s", nccl().why.c_str());
+  int rc = nccl().CommDestroy(static_cast<ncclComm_t>(comm));
+  if (rc != ncclSuccess_) return nccl_fail(rc, "ncclCommDestroy");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_allreduce_max(void* comm, void* values, int64_t count, int dtype, void* stream) {
+  if (!comm || !values || count < 1) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "bad all-reduce arguments");
+  if (dtype != EXAHYPE_DTYPE_F64 && dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  if (!nccl().handle) return fail(EXAHYPE_ERR_UNAVAILABLE, "%s", nccl().why.c_str());
+  int rc = nccl().AllReduce(values, values, (size_t)count, dtype == EXAHYPE_DTYPE_F64 ? ncclFloat64_ : ncclFloat32_,
+                            ncclMax_, static_cast<ncclComm_t>(comm), static_cast<cudaStream_t>(stream));
+  if (rc != ncclSuccess_) return nccl_fail(rc, "ncclAllReduce(max)");
+  return EXAHYPE_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

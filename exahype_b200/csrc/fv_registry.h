@@ -1,0 +1,46 @@
+// Table of committed kernel instantiations; each translation unit inst_*.cu contributes one array.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/exahype_cuda.h"
+#include "fv_patch_kernel.cuh"
+
+namespace exahype {
+
+using FvLaunchFn = cudaError_t (*)(const void*, void*, long long, double, void*, void*, cudaStream_t);
+using FvPrepareFn = cudaError_t (*)(FvLaunchInfo*, long long);
+
+struct FvEntry {
+  exahype_fv_config cfg;      // flags == 0; the variant is picked from the caller's flags
+  FvLaunchFn launch[4];       // index = (DISSIPATION_ALL ? 1 : 0) | (OUTPUT_UNHALOED ? 2 : 0)
+  FvPrepareFn prepare[4];
+};
+
+struct FvEntryList {
+  const FvEntry* entries;
+  int count;
+};
+
+FvEntryList euler2d_entries();
+FvEntryList euler3d_entries();
+FvEntryList swe2d_entries();
+
+#define EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, DA, UH) \
+  ::exahype::FvKernelConfig<PHYS, ::exahype::RusanovUpdate, T, DIM, P, H, G, NT, MINB, DA, UH>
+
+// one committed shape = four kernels (dissipation var0|all  x  output haloed|un-haloed)
+#define EXAHYPE_FV_ENTRY(MODEL, DTYPE, PHYS, T, DIM, P, H, G, NT, MINB)                                   \
+  {                                                                                                       \
+    {MODEL, DTYPE, DIM, P, H, PHYS::NR, PHYS::NA, 0u},                                                    \
+        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, false)>::launch,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, false)>::launch,    \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, true)>::launch,    \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, true)>::launch},    \
+        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, false)>::prepare,  \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, false)>::prepare,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, true)>::prepare,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, true)>::prepare}    \
+  }
+
+}  // namespace exahype

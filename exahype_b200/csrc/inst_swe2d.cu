@@ -1,0 +1,18 @@
+// Committed instantiations: 2-D shallow water (h, hu, hv | bathymetry), fp64 and fp32.
+// BASELINE.json config C4: 32x32 patches + 1 halo -- 1024 interior cells, two per thread.
+#include "fv_registry.h"
+
+namespace exahype {
+namespace {
+using SW = SwePhysics<3, 1>;
+
+const FvEntry kEntries[] = {
+    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 2, 32, 1, 1, 512, 1),
+    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 2, 32, 1, 1, 512, 1),
+    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 2, 16, 1, 1, 256, 2),
+    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 2, 16, 1, 1, 256, 2),
+};
+}  // namespace
+
+FvEntryList swe2d_entries() { return {kEntries, (int)(sizeof(kEntries) / sizeof(kEntries[0]))}; }
+}  // namespace exahype

@@ -1,0 +1,554 @@
+"""``CUDAPrinter`` -- turns a :class:`KernelBuilder` declaration into a CUDA translation unit for sm_100a.
+
+Where the reference's ``CPPPrinter`` (``exahype/printers/CPPPrinter.py:48-102``) prints one serial loop nest per
+statement plus five heap temporaries, this back-end recognises the *program* those statements form -- the batched
+stateless finite-volume Rusanov update of ``examples/Batched_stateless.py:25-35`` -- and emits
+
+* ``__device__`` functors for the declared flux / eigenvalue functions (hand-written family, SymPy expressions, or
+  the user's own device source with the reference's ``Functions.h`` signatures),
+* an update functor whose two expressions are printed from the declaration's own statements in SymPy's ``str``
+  order, i.e. the evaluation order the reference's generated C++ has, and
+* an ``extern "C"`` entry that instantiates the hand-written kernel template ``csrc/fv_patch_kernel.cuh`` for the
+  declared geometry.
+
+``.code`` / ``.file()`` / ``.here()`` / ``.loop()`` follow ``CodePrinter`` (reference ``CodePrinter.py:46-71``);
+``.build()`` compiles the unit with nvcc and returns a callable bound through ctypes.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import sympy
+from sympy import Idx, Indexed, Symbol
+from sympy.printing.c import C99CodePrinter
+from sympy.printing.str import StrPrinter
+
+from ..KernelBuilder import KernelBuilder
+from ..TypedFunction import DeviceBody
+from .CodePrinter import CodePrinter
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+INCLUDE = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "include")
+
+_SMEM_LIMIT = 227 * 1024
+
+
+class UnsupportedKernel(NotImplementedError):
+    """The declaration is not the batched stateless Rusanov patch update this back-end accelerates."""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class RusanovProgram:
+    """What the statement list means, after pattern recognition."""
+    q_in: str                     # declared input / output item (reference: 'Q')
+    q_work: str                   # working copy (reference: 'Q_copy')
+    flux_tmp: str                 # directional item receiving the flux
+    eigen_tmp: str                # directional item receiving the eigenvalue
+    flux_fn: str
+    eigen_fn: str
+    max_fn: Optional[str]
+    normal: str                   # directional const passed to the functions
+    normals: List[int]            # its value per axis
+    dt: Optional[str]
+    flux_update: str              # device expression in (qc, f_plus, f_minus)
+    dissipation: str              # device expression in (qc, q0, q_plus, q_minus, l0, l_plus, l_minus, dt)
+    dissipation_all: bool         # False: variable 0 only, as the reference emits
+    roles: List[str] = field(default_factory=list)   # one label per statement, for the listing
+
+
+class _StatementPrinter(StrPrinter):
+    """Prints a statement's RHS as a C++ expression in SymPy ``str`` order -- the order the reference's CPPPrinter
+    emits (it prints ``str(expr)``) -- with array accesses replaced by the kernel template's local names."""
+
+    printmethod = "_exahype_device_str"   # Indexed._sympystr would otherwise bypass _print_Indexed
+
+    def __init__(self, names: Dict[Indexed, str], max_fn: Optional[str]):
+        super().__init__()
+        self._names = names
+        self._max_fn = max_fn
+
+    def _print_Indexed(self, expr):
+        if expr not in self._names:
+            raise UnsupportedKernel(f"unexpected array access {expr} in an update statement")
+        return self._names[expr]
+
+    def _print_Float(self, expr):
+        return f"T({repr(float(expr))})"
+
+    def _print_Integer(self, expr):
+        return str(int(expr))
+
+    def _print_Idx(self, expr):
+        return str(expr.label)
+
+    def _print_Rational(self, expr):
+        return f"(T({int(expr.p)})/T({int(expr.q)}))"
+
+    def _print_Pow(self, expr, rational=False):
+        raise UnsupportedKernel("powers are not supported in update statements (the reference emits str(expr))")
+
+    def _print_Function(self, expr):
+        name = expr.func.__name__
+        args = ", ".join(self._print(a) for a in expr.args)
+        if name == self._max_fn and len(expr.args) == 2:
+            return f"::exahype::fv_max({args})"          # reference: double max(double*, double*), Functions.cpp:64-66
+        raise UnsupportedKernel(f"call to {name} inside an update statement")
+
+
+def _offset_on_axis(access: Indexed, kernel: KernelBuilder, axis: int) -> int:
+    """Offset of ``access`` along sweep axis ``axis`` (1-based); every other index must be un-shifted."""
+    off = 0
+    for level, idx in enumerate(access.indices):
+        if level >= 1 + kernel.dim:
+            break
+        base = kernel.all_items[str(kernel.indexes[level])]
+        delta = sympy.simplify(idx - base)
+        if not delta.is_Integer:
+            raise UnsupportedKernel(f"index {idx} of {access} is not a constant offset")
+        if int(delta) != 0:
+            if level != axis:
+                raise UnsupportedKernel(f"{access} is shifted off the sweep axis")
+            off = int(delta)
+    return off
+
+
+def analyse(kernel: KernelBuilder) -> RusanovProgram:
+    """Recognise the Rusanov patch-update program in ``kernel``'s statement list, or raise."""
+    k = kernel
+    if len(k.items) < 2 or len(k.directional_items) < 2:
+        raise UnsupportedKernel("expected two items (input, working copy) and two directional items (flux, eigenvalue)")
+    stmts = list(zip(k.LHS, k.RHS, k.directions, k.struct_inclusion))
+    roles: List[str] = []
+    dim = k.dim
+
+    def base_of(e) -> str:
+        return str(e.base) if isinstance(e, Indexed) else ""
+
+    def fn_name(e) -> str:
+        return e.func.__name__ if isinstance(e, sympy.Function) and e.func.__name__ in k.functions else ""
+
+    # --- copy-in / copy-out ------------------------------------------------------------------------------------
+    first, last = stmts[0], stmts[-1]
+    if not (isinstance(first[0], Indexed) and isinstance(first[1], Indexed) and first[2] in (-1, -2)):
+        raise UnsupportedKernel("first statement must copy the input into the working item")
+    q_work, q_in = base_of(first[0]), base_of(first[1])
+    if not (isinstance(last[0], Indexed) and base_of(last[0]) == q_in and base_of(last[1]) == q_work):
+        raise UnsupportedKernel("last statement must copy the working item back into the input")
+
+    flux_calls, eig_calls, flux_upd, diss_upd = {}, {}, {}, {}
+    normal_name, normals = None, {}
+    pending_normal = None
+    for pos, (lhs, rhs, direction, struct) in enumerate(stmts):
+        if pos == 0:
+            roles.append("copy-in"); continue
+        if pos == len(stmts) - 1:
+            roles.append("copy-out"); continue
+        if struct == -1 and isinstance(lhs, Symbol) and str(lhs) in k.directional_consts:
+            normal_name = str(lhs); pending_normal = int(rhs); roles.append(f"{lhs} = {rhs}"); continue
+        if fn_name(lhs) and rhs is None:                                   # Flux(Qc[c], normal, F_d[c])
+            args = lhs.args
+            if len(args) < 3 or base_of(args[0]) != q_work or not isinstance(args[-1], Indexed):
+                raise UnsupportedKernel(f"flux call {lhs} must be f({q_work}[c], {normal_name}, tmp[c])")
+            flux_calls[direction] = (fn_name(lhs), base_of(args[-1]), pending_normal)
+            roles.append(f"flux axis {direction}"); continue
+        if isinstance(lhs, Indexed) and fn_name(rhs):                      # L_d[c] = maxEigenvalue(Qc[c], normal)
+            if base_of(rhs.args[0]) != q_work:
+                raise UnsupportedKernel(f"eigenvalue call {rhs} must read {q_work}[c]")
+            eig_calls[direction] = (fn_name(rhs), base_of(lhs), pending_normal)
+            roles.append(f"eigenvalue axis {direction}"); continue
+        if isinstance(lhs, Indexed) and base_of(lhs) == q_work and isinstance(rhs, sympy.Expr):
+            used = {base_of(a) for a in rhs.atoms(Indexed)}
+            if any(b.startswith(tuple(k.directional_items)) for b in used) and q_in not in used:
+                flux_upd[direction] = (lhs, rhs, struct); roles.append(f"flux update axis {direction}"); continue
+            if q_in in used:
+                diss_upd[direction] = (lhs, rhs, struct); roles.append(f"dissipation axis {direction}"); continue
+        raise UnsupportedKernel(f"statement {pos} ({lhs} = {rhs}) is not part of the Rusanov patch update")
+
+    axes = list(range(1, dim + 1))
+    for table, what in ((flux_calls, "flux call"), (eig_calls, "eigenvalue call"), (flux_upd, "flux update"),
+                        (diss_upd, "dissipation update")):
+        if sorted(table) != axes:
+            raise UnsupportedKernel(f"need exactly one {what} per axis, got axes {sorted(table)}")
+    flux_fn = {v[0] for v in flux_calls.values()}
+    eigen_fn = {v[0] for v in eig_calls.values()}
+    if len(flux_fn) != 1 or len(eigen_fn) != 1:
+        raise UnsupportedKernel("one flux and one eigenvalue function expected")
+    suffix = ("", "_x", "_y", "_z")
+    flux_tmp = flux_calls[1][1][: -len(suffix[1])]
+    eigen_tmp = eig_calls[1][1][: -len(suffix[1])]
+    for d in axes:
+        if flux_calls[d][1] != flux_tmp + suffix[d] or eig_calls[d][1] != eigen_tmp + suffix[d]:
+            raise UnsupportedKernel("directional temporaries are not used consistently across axes")
+        normals[d] = flux_calls[d][2]
+        if normals[d] is None or eig_calls[d][2] != normals[d]:
+            raise UnsupportedKernel("the directional constant must be set ahead of each sweep")
+    if [normals[d] for d in axes] != list(range(dim)):
+        raise UnsupportedKernel("kernel template pairs sweep axis d with normal d-1 (reference Batched_stateless.py:17)")
+
+    # --- update expressions, printed per axis and required to be the same program on every axis -----------------
+    max_candidates = [f for f in k.functions if f not in (next(iter(flux_fn)), next(iter(eigen_fn)))]
+    dt_names = [n for n in k.inputs]
+
+    def names_for(rhs, d):
+        names = {}
+        for a in rhs.atoms(Indexed):
+            b, off = base_of(a), _offset_on_axis(a, k, d)
+            tag = {0: "0", 1: "plus", -1: "minus"}.get(off)
+            if tag is None:
+                raise UnsupportedKernel(f"{a}: only offsets -1, 0, +1 are supported (one halo layer)")
+            if b == q_work and off == 0:
+                names[a] = "qc"
+            elif b == q_in:
+                names[a] = "q0" if off == 0 else f"q_{tag}"
+            elif b == flux_tmp + suffix[d] and off != 0:
+                names[a] = f"f_{tag}"
+            elif b == eigen_tmp + suffix[d]:
+                names[a] = "l0" if off == 0 else f"l_{tag}"
+            else:
+                raise UnsupportedKernel(f"unexpected access {a} in the update along axis {d}")
+        return names
+
+    def printed(table, allowed_syms):
+        texts = set()
+        max_fn = None
+        for d in axes:
+            lhs, rhs, _ = table[d]
+            if _offset_on_axis(lhs, k, d) != 0:
+                raise UnsupportedKernel("updates must write the centre cell")
+            used_fns = {f.func.__name__ for f in rhs.atoms(sympy.Function) if f.func.__name__ in k.functions}
+            if len(used_fns) > 1 or not used_fns <= set(max_candidates):
+                raise UnsupportedKernel(f"unexpected function calls {used_fns} in an update")
+            max_fn = next(iter(used_fns)) if used_fns else max_fn
+            inside_accesses = set().union(*[a.free_symbols for a in rhs.atoms(Indexed)]) if rhs.atoms(Indexed) else set()
+            for sym in rhs.free_symbols - inside_accesses:
+                if str(sym) not in allowed_syms:
+                    raise UnsupportedKernel(f"symbol {sym} is not available inside the kernel")
+            texts.add(_StatementPrinter(names_for(rhs, d), max_fn).doprint(rhs))
+        if len(texts) != 1:
+            raise UnsupportedKernel(f"the update differs between axes: {sorted(texts)}")
+        return texts.pop(), max_fn
+
+    flux_text, _ = printed(flux_upd, set())
+    diss_text, max_fn = printed(diss_upd, set(dt_names))
+    dt = next((n for n in dt_names if Symbol(n) in diss_upd[1][1].free_symbols
+               or any(str(s) == n for s in diss_upd[1][1].free_symbols)), None)
+    if dt is not None and dt != "dt":
+        diss_text = diss_text.replace(dt, "dt")
+
+    # var extent of the dissipation exactly as the reference's printer decides it (CPPPrinter.py:118-126):
+    # min over the statement's struct code and every item_struct name that is a substring of the statement
+    lhs, rhs, struct = diss_upd[1]
+    widths = [w for name, w in k.item_struct.items() if name in str([lhs, rhs])] + [struct]
+    dissipation_all = min(widths) >= 1
+
+    return RusanovProgram(q_in=q_in, q_work=q_work, flux_tmp=flux_tmp, eigen_tmp=eigen_tmp,
+                          flux_fn=next(iter(flux_fn)), eigen_fn=next(iter(eigen_fn)), max_fn=max_fn,
+                          normal=normal_name or "normal", normals=[normals[d] for d in axes], dt=dt,
+                          flux_update=flux_text, dissipation=diss_text, dissipation_all=dissipation_all, roles=roles)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def smem_bytes(dim, P, H, nr, na, G, elem, diss_all, unhaloed_unused=False) -> int:
+    """Python mirror of ``FvKernelConfig::SMEM_BYTES`` (csrc/fv_patch_kernel.cuh)."""
+    up = lambda x, a: (x + a - 1) // a * a
+    nv, S = nr + na, P + 2 * H
+    ncell, pd, pf = S ** dim, P ** dim, P ** (dim - 1)
+    patch_bytes = ncell * nv * elem
+    qbuf = 2 if patch_bytes % 16 == 0 else 1
+    slots = (P + 2) * pf
+    dv = nr if diss_all else 1
+    off_f = up(qbuf * G * patch_bytes, 16)
+    off_l = up(off_f + dim * nr * G * slots * elem, 16)
+    off_r = up(off_l + dim * G * slots * elem, 16)
+    off_out = up(off_r + (dv * G * ncell * elem if nv % 2 == 0 else 0), 128)
+    off_lam = up(off_out + G * pd * nv * elem, 16)
+    off_bar = up(off_lam + 2 * G * 8, 16)
+    return off_bar + 16
+
+
+def pick_geometry(dim, P, H, nr, na, elem):
+    """(patches per tile G, threads per CTA, min CTAs/SM): about one thread per interior cell, 128..512 threads."""
+    pd = P ** dim
+    if pd >= 1024:
+        G, nt = 1, 512
+    elif pd >= 128:
+        G, nt = 1, (pd + 31) // 32 * 32
+    else:
+        G = max(1, 256 // pd)
+        nt = min(256, (G * pd + 31) // 32 * 32)
+    while G > 1 and smem_bytes(dim, P, H, nr, na, G, elem, True) > _SMEM_LIMIT // 2:
+        G -= 1
+    if smem_bytes(dim, P, H, nr, na, G, elem, True) > _SMEM_LIMIT:
+        raise UnsupportedKernel(f"a {P}^{dim} patch with {nr + na} variables does not fit 227 KB of shared memory")
+    minb = max(1, min(4, _SMEM_LIMIT // smem_bytes(dim, P, H, nr, na, G, elem, True), 65536 // (nt * 128)))
+    return G, nt, minb
+
+
+class _DevicePrinter(C99CodePrinter):
+    """SymPy expression -> C++ over the template type ``T``."""
+
+    def _print_Float(self, expr):
+        return f"T({repr(float(expr))})"
+
+    def _print_Rational(self, expr):
+        return f"(T({int(expr.p)})/T({int(expr.q)}))"
+
+    def _print_Abs(self, expr):
+        return f"::exahype::fv_abs<T>({self._print(expr.args[0])})"
+
+    def _print_Pow(self, expr):
+        b, e = expr.args
+        if e == sympy.Rational(1, 2):
+            return f"::exahype::fv_sqrt<T>({self._print(b)})"
+        if e == -1:
+            return f"(T(1.0)/({self._print(b)}))"
+        if e == sympy.Rational(-1, 2):
+            return f"(T(1.0)/::exahype::fv_sqrt<T>({self._print(b)}))"
+        if e.is_Integer and 2 <= int(e) <= 4:
+            return "(" + "*".join([f"({self._print(b)})"] * int(e)) + ")"
+        return f"pow({self._print(b)}, {self._print(e)})"
+
+    def _print_Max(self, expr):
+        args = [self._print(a) for a in expr.args]
+        out = args[0]
+        for a in args[1:]:
+            out = f"::exahype::fv_max<T>({out}, {a})"
+        return out
+
+
+class CUDAPrinter(CodePrinter):
+    """``CUDAPrinter(kernel, function_name="time_step", dtype="f64")``.
+
+    dtype        'f64' | 'f32' -- arithmetic type of the generated entry.
+    dissipation  None: as the reference's printer would emit it (variable 0 only for the reference declaration,
+                 CPPPrinter.py:118-126); 'all' / 'var0' to force.
+    model        'euler' | 'swe': use a committed hand-written functor family for functions declared without a body.
+    """
+
+    def __init__(self, kernel: KernelBuilder, function_name: str = "time_step", dtype: str = "f64",
+                 dissipation: Optional[str] = None, model: Optional[str] = None,
+                 patches_per_tile: Optional[int] = None, threads: Optional[int] = None):
+        super().__init__(kernel, function_name=function_name)
+        if dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
+        if kernel.halo_size < 1:
+            raise UnsupportedKernel("the Rusanov update reads one halo layer: halo_size must be >= 1")
+        self.dtype = dtype
+        self.ctype = "double" if dtype == "f64" else "float"
+        self.program = analyse(kernel)
+        if dissipation not in (None, "all", "var0"):
+            raise ValueError("dissipation must be None, 'all' or 'var0'")
+        self.dissipation_all = self.program.dissipation_all if dissipation is None else dissipation == "all"
+        self.model = model
+        k = kernel
+        elem = 8 if dtype == "f64" else 4
+        G, nt, minb = pick_geometry(k.dim, k.patch_size, k.halo_size, k.n_real, k.n_aux, elem)
+        self.patches_per_tile = patches_per_tile or G
+        self.threads = threads or nt
+        self.min_ctas = minb
+        self.header_file_name: Optional[str] = None
+        self._statements: List[str] = []
+        self.code = self._emit()
+
+    # ------------------------------------------------------------------ CodePrinter interface
+    def loop(self, expr: list, direction: int, below: int = 0, struct_inclusion: int = 0):
+        """One statement -> one line of the listing placed at the top of the unit: on the GPU a statement is not a
+        loop nest but a phase of the fused kernel (see csrc/fv_patch_kernel.cuh)."""
+        role = self.program.roles[len(self._statements)] if len(self._statements) < len(self.program.roles) else "?"
+        lhs, rhs = expr
+        text = f"{lhs};" if rhs is None or rhs == '' else f"{lhs} = {rhs};"
+        phase = {"copy-in": "TMA bulk load of the tile into shared memory", "copy-out": "phase C: staged interior -> HBM"}.get(
+            role, "phase A: per-cell functor" if role.startswith(("flux axis", "eigen")) else
+            "phase B: register update" if "update" in role or "dissipation" in role else "compile-time axis")
+        line = f"//   [{len(self._statements):2d}] dir={direction:2d} struct={struct_inclusion:2d}  {role:<22s} -> {phase}\n//        {text}\n"
+        self._statements.append(line)
+        return line
+
+    def file(self, file_name: str = "time_step.cu", header_file_name: Optional[str] = None):
+        """Write the unit; ``header_file_name`` is #included first and must define the declared functions as device
+        code with the reference's signatures (``Unit test/Functions.h:2-4``) when they have no body attached."""
+        if header_file_name != self.header_file_name:
+            self.header_file_name = header_file_name
+            self._statements = []
+            self.code = self._emit()
+        super().file(file_name, header_file_name)
+
+    # ------------------------------------------------------------------ emission
+    def _body_of(self, name: str) -> Optional[DeviceBody]:
+        fn = self.kernel().all_items.get(name)
+        body = getattr(fn, "device_body", None)
+        if body is None and self.model is not None:
+            body = DeviceBody(builtin=self.model)
+        return body
+
+    def _physics(self) -> str:
+        k, p = self.kernel(), self.program
+        nr, na, nv, dim = k.n_real, k.n_aux, k.n_real + k.n_aux, k.dim
+        fb, eb = self._body_of(p.flux_fn), self._body_of(p.eigen_fn)
+        if fb is not None and fb.builtin and (eb is None or eb.builtin == fb.builtin):
+            fam = fb.builtin
+            if fam == "euler":
+                return f"using Physics = ::exahype::EulerPhysics<{dim}, {nr}, {na}>;   // csrc/physics.cuh\n"
+            if fam == "swe":
+                if dim != 2:
+                    raise UnsupportedKernel("the shallow-water family is 2-D")
+                return f"using Physics = ::exahype::SwePhysics<{nr}, {na}>;   // csrc/physics.cuh\n"
+            raise UnsupportedKernel(f"unknown builtin physics '{fam}'")
+
+        out = [f"struct Physics {{\n  static constexpr int NR = {nr}, NA = {na}, NV = {nv};\n"
+               "  template <typename T> struct Prims {};\n"
+               "  template <typename T> static __device__ __forceinline__ Prims<T> prims(const T (&)[NV]) { return {}; }\n"]
+        q = sympy.symbols(f"q0:{nv}", real=True)
+        prn = _DevicePrinter()
+
+        def lower(expr):
+            text = prn.doprint(sympy.sympify(expr))
+            for v in reversed(range(nv)):
+                text = text.replace(f"q{v}", f"q[{v}]")
+            return text
+
+        # flux
+        out.append("  template <int N, typename T>\n"
+                   "  static __device__ __forceinline__ void flux(const T (&q)[NV], const Prims<T>&, T (&F)[NR]) {\n")
+        if fb is not None and fb.expressions:
+            for n in range(dim):
+                comps = list(fb.expressions(list(q), n))
+                if len(comps) != nr:
+                    raise ValueError(f"{p.flux_fn}: expected {nr} flux components, got {len(comps)}")
+                out.append(f"    if (N == {n}) {{\n" + "".join(f"      F[{v}] = {lower(c)};\n" for v, c in enumerate(comps)) + "    }\n")
+        else:   # user's device function with the reference signature: void Flux(const T* Q, int normal, T* F)
+            out.append(f"    {p.flux_fn}(q, N, F);\n")
+        out.append("  }\n")
+        # eigenvalue
+        out.append("  template <int N, typename T>\n"
+                   "  static __device__ __forceinline__ T eigen(const T (&q)[NV], const Prims<T>&) {\n")
+        if eb is not None and eb.expressions:
+            for n in range(dim):
+                out.append(f"    if (N == {n}) return {lower(eb.expressions(list(q), n))};\n")
+            out.append("    return T(0);\n")
+        else:
+            out.append(f"    return {p.eigen_fn}(q, N);\n")
+        out.append("  }\n};\n")
+        pre = ""
+        for b in (fb, eb):
+            if b is not None and b.source and b.source not in pre:
+                pre += b.source.rstrip() + "\n\n"
+        return pre + "".join(out)
+
+    def _emit(self) -> str:
+        k, p = self.kernel(), self.program
+        self._statements = []
+        for lhs, rhs, d, s in zip(k.LHS, k.RHS, k.directions, k.struct_inclusion):
+            self.loop([lhs, rhs], d, k.dim + 1, s)
+        T = self.ctype
+        fname = self.functionName()
+        cfg = lambda da, uh: (f"::exahype::FvKernelConfig<Physics, Update, {T}, {k.dim}, {k.patch_size}, {k.halo_size}, "
+                              f"{self.patches_per_tile}, {self.threads}, {self.min_ctas}, {str(da).lower()}, {str(uh).lower()}>")
+        da = self.dissipation_all
+        parts = []
+        if self.header_file_name:
+            parts.append(f'#include "{self.header_file_name}"\n')
+        parts.append(
+            "// Generated by exahype.printers.CUDAPrinter -- do not edit.\n"
+            f"// Kernel: dim={k.dim} patch_size={k.patch_size} halo_size={k.halo_size} n_real={k.n_real} n_aux={k.n_aux}; "
+            f"dtype={self.dtype}; dissipation={'all' if da else 'var0'}\n"
+            "// Statement list (KernelBuilder) and where each statement went in the fused kernel:\n"
+            + "".join(self._statements) +
+            "#include <stdint.h>\n#include <cuda_runtime.h>\n#include \"fv_patch_kernel.cuh\"\n\nnamespace {\n\n")
+        parts.append(self._physics())
+        parts.append(
+            "\n// update statements in the evaluation order of the declaration (SymPy str order == reference C++ order)\n"
+            "struct Update {\n"
+            "  template <typename T>\n"
+            "  static __device__ __forceinline__ T flux(T qc, T f_plus, T f_minus) {\n"
+            f"    return {p.flux_update};\n  }}\n"
+            "  template <typename T>\n"
+            "  static __device__ __forceinline__ T dissipation(T qc, T q0, T q_plus, T q_minus, T l0, T l_plus, T l_minus, T dt) {\n"
+            f"    return {p.dissipation};\n  }}\n}};\n\n}}  // namespace\n\n")
+        parts.append(
+            f"// Drop-in for the reference's generated `void {fname}(double* Q, double dt)` over a device-resident batch.\n"
+            "// flags: bit 1 = un-haloed output, bit 2 = accumulate into *lambda_max (include/exahype_cuda.h).\n"
+            f'extern "C" __attribute__((visibility("default")))\n'
+            f"int {fname}(const void* q_in, void* q_out, int64_t n_patches, double dt, void* lambda_patch, void* lambda_max,\n"
+            f"    unsigned flags, void* stream) {{\n"
+            "  cudaStream_t s = static_cast<cudaStream_t>(stream);\n"
+            f"  if (lambda_max && !(flags & 4u) && cudaMemsetAsync(lambda_max, 0, sizeof({T}), s) != cudaSuccess) return -3;\n"
+            "  if (n_patches <= 0) return n_patches < 0 ? -1 : 0;\n"
+            "  if (!q_in || !q_out || ((uintptr_t)q_in & 15) || ((uintptr_t)q_out & 15)) return -1;\n"
+            "  cudaError_t err = (flags & 2u)\n"
+            f"      ? ::exahype::FvLauncher<{cfg(da, True)}>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s)\n"
+            f"      : ::exahype::FvLauncher<{cfg(da, False)}>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);\n"
+            "  return err == cudaSuccess ? 0 : -3;\n}\n")
+        return "".join(parts)
+
+    # ------------------------------------------------------------------ compile + bind
+    def build(self, directory: Optional[str] = None, include_dirs=(), verbose: bool = False) -> "GeneratedKernel":
+        """nvcc the unit for sm_100a into a shared library (cross-compiles without a GPU) and bind it."""
+        from .. import build as _b
+        directory = directory or os.path.join(tempfile.gettempdir(), "exahype_b200_generated")
+        os.makedirs(directory, exist_ok=True)
+        tag = hashlib.sha1(self.code.encode()).hexdigest()[:16]
+        src = os.path.join(directory, f"{self.functionName()}_{tag}.cu")
+        lib = os.path.join(directory, f"lib{self.functionName()}_{tag}.so")
+        if not os.path.exists(lib):
+            with open(src, "w") as f:
+                f.write(self.code)
+            cmd = [_b.nvcc()] + _b.NVCC_FLAGS + _b._host_compiler_args() + ["-I", CSRC, "-I", INCLUDE]
+            for d in include_dirs:
+                cmd += ["-I", d]
+            cmd += ["-shared", src, "-o", lib + ".tmp", "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode:
+                raise RuntimeError(f"nvcc failed on the generated kernel:\n{r.stderr}")
+            os.replace(lib + ".tmp", lib)
+        return GeneratedKernel(self, lib)
+
+
+class GeneratedKernel:
+    """A compiled ``CUDAPrinter`` unit: same ``step`` call as :class:`exahype_b200.runtime.PatchUpdate`."""
+
+    def __init__(self, printer: CUDAPrinter, lib_path: str):
+        k = printer.kernel()
+        self.lib_path = lib_path
+        self.dim, self.patch_size, self.halo_size = k.dim, k.patch_size, k.halo_size
+        self.n_real, self.n_aux, self.dtype = k.n_real, k.n_aux, printer.dtype
+        self._lib = ctypes.CDLL(lib_path)
+        self._fn = getattr(self._lib, printer.functionName())
+        vp = ctypes.c_void_p
+        self._fn.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_uint, vp]
+        self._fn.restype = ctypes.c_int
+
+    def in_shape(self, n):
+        return (n,) + (self.patch_size + 2 * self.halo_size,) * self.dim + (self.n_real + self.n_aux,)
+
+    def out_shape(self, n, unhaloed=False):
+        return (n,) + (self.patch_size,) * self.dim + (self.n_real + self.n_aux,) if unhaloed else self.in_shape(n)
+
+    def step(self, q_in, q_out=None, dt: float = 0.0, lambda_patch=None, lambda_max=None, stream=None,
+             unhaloed: bool = False, accumulate_lambda: bool = False):
+        import torch
+        if q_out is None:
+            q_out = q_in
+        per = (self.patch_size + 2 * self.halo_size) ** self.dim * (self.n_real + self.n_aux)
+        if q_in.numel() % per or not q_in.is_cuda or not q_in.is_contiguous():
+            raise ValueError("q_in must be a contiguous CUDA tensor holding whole patches")
+        n = q_in.numel() // per
+        if stream is None:
+            stream = torch.cuda.current_stream(q_in.device).cuda_stream
+        flags = (2 if unhaloed else 0) | (4 if accumulate_lambda else 0)
+        with torch.cuda.device(q_in.device):
+            rc = self._fn(q_in.data_ptr(), q_out.data_ptr(), n, float(dt),
+                          lambda_patch.data_ptr() if lambda_patch is not None else None,
+                          lambda_max.data_ptr() if lambda_max is not None else None, flags, stream)
+        if rc:
+            raise RuntimeError(f"generated kernel failed with code {rc}")
+        return q_out

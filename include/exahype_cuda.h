@@ -1,0 +1,141 @@
+/*
+ * libexahype_cuda.so -- C ABI of the B200-native batched stateless finite-volume Rusanov patch update.
+ *
+ * This is the drop-in boundary for ONE path of xdslproject/ExaHyPE: the generated kernel
+ *     void time_step(double* Q, double dt);                 (reference: Unit test/test.h:3,
+ *                                                            body Unit test/test.cpp:3-111,
+ *                                                            emitted by exahype/printers/CPPPrinter.py:48-102)
+ * together with the user physics it links against
+ *     void   Flux(const double* Q, int normal, double* F);  (reference: Unit test/Functions.h:2)
+ *     double maxEigenvalue(const double* Q, int normal);    (reference: Unit test/Functions.h:3)
+ *     double max(double* a, double* b);                     (reference: Unit test/Functions.h:4)
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Device entry points take DEVICE pointers and a
+ * cudaStream_t passed as void*; they are asynchronous and allocate nothing.  Every function returns
+ * EXAHYPE_OK (0) or a negative error code; exahype_cuda_last_error() gives the thread-local message.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with EXAHYPE_ERR_CUDA.
+ *
+ * Data layout (reference: exahype/printers/CPPPrinter.py:247-261, Unit test/test.cpp:15):
+ *     Q[patch][i][j]([k])[var]   AoS, haloed, side S = patch_size + 2*halo, var < n_real + n_aux,
+ *     `i` slowest spatial index and paired with normal = 0.
+ */
+#ifndef EXAHYPE_CUDA_H
+#define EXAHYPE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXAHYPE_CUDA_ABI_VERSION 1
+
+enum {
+  EXAHYPE_OK = 0,
+  EXAHYPE_ERR_INVALID_ARGUMENT = -1, /* mirrors KernelBuilder.viable() (reference KernelBuilder.py:41-48) + pointer/size checks */
+  EXAHYPE_ERR_NO_INSTANTIATION = -2, /* no committed kernel for this (model, dim, patch, halo, vars, dtype): generate one with CUDAPrinter */
+  EXAHYPE_ERR_CUDA = -3,             /* CUDA runtime error (message carries cudaGetErrorString) */
+  EXAHYPE_ERR_NCCL = -4,
+  EXAHYPE_ERR_UNAVAILABLE = -5       /* optional component missing (e.g. libnccl not loadable) */
+};
+
+/* physics families with committed hand-written functors (csrc/physics.cuh) */
+enum { EXAHYPE_MODEL_EULER = 0, EXAHYPE_MODEL_SWE = 1 };
+enum { EXAHYPE_DTYPE_F64 = 0, EXAHYPE_DTYPE_F32 = 1 };
+
+/* flags */
+enum {
+  /* Rusanov dissipation on all n_real unknowns (what `struct=True` at examples/Batched_stateless.py:33 intends).
+   * Default (flag clear) is the reference-emitted behaviour: variable 0 only (Unit test/test.cpp:81,90). */
+  EXAHYPE_FLAG_DISSIPATION_ALL = 1u << 0,
+  /* q_out is un-haloed: q_out[patch][P]^dim[n_real+n_aux] (ExaHyPE2's QOut convention, reference
+   * exahype/printers/CPPPrinter.py:255-258, examples/kernel-generator.py:11-12).  Default: q_out has the haloed
+   * layout of q_in and only interior cells are written (q_out == q_in gives the reference's in-place update). */
+  EXAHYPE_FLAG_OUTPUT_UNHALOED = 1u << 1,
+  /* do not reset *lambda_max to 0 before the launch: fold this launch into the running maximum */
+  EXAHYPE_FLAG_LAMBDA_ACCUMULATE = 1u << 2
+};
+
+typedef struct {
+  int32_t model;      /* EXAHYPE_MODEL_* */
+  int32_t dtype;      /* EXAHYPE_DTYPE_* */
+  int32_t dim;        /* 2 | 3 */
+  int32_t patch_size; /* P */
+  int32_t halo;       /* h >= 1 */
+  int32_t n_real;
+  int32_t n_aux;
+  uint32_t flags;     /* EXAHYPE_FLAG_* */
+} exahype_fv_config;
+
+int exahype_cuda_version(void);
+const char* exahype_cuda_last_error(void);
+/* number of visible CUDA devices (0 on a host without a GPU; never fails) */
+int exahype_cuda_device_count(void);
+/* 1 if a committed instantiation exists for cfg (ignores flags), else 0 */
+int exahype_cuda_fv_supported(const exahype_fv_config* cfg);
+/* Fills up to `capacity` configs with the committed instantiations; returns how many exist. */
+int exahype_cuda_fv_list(exahype_fv_config* out, int capacity);
+
+/*
+ * One patch-update step over a batch resident in device memory: replaces `time_step(Q, dt)`
+ * (reference Unit test/test.h:3) for n_patches patches at once.
+ *   q_in          device, haloed AoS batch, n_patches * S^dim * (n_real+n_aux) elements of cfg->dtype, 16-byte aligned
+ *   q_out         device; == q_in for the reference's in-place semantics, or a second buffer (haloed or un-haloed per flags)
+ *   dt            time step (converted to cfg->dtype)
+ *   lambda_patch  device, nullable: n_patches values, max over interior cells and directions of maxEigenvalue(Q_in)
+ *   lambda_max    device, nullable: 1 value, max over the batch (reset to 0 first unless EXAHYPE_FLAG_LAMBDA_ACCUMULATE)
+ *   stream        cudaStream_t
+ */
+int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q_out, int64_t n_patches,
+                         double dt, void* lambda_patch, void* lambda_max, void* stream);
+
+/* Named entry points for the committed headline instantiations (same semantics as exahype_cuda_fv_step). */
+int exahype_cuda_fv_step_euler_2d_f64(const double* q_in, double* q_out, int64_t n_patches, int patch_size, int halo,
+                                      int n_aux, double dt, double* lambda_patch, double* lambda_max,
+                                      unsigned flags, void* stream);
+int exahype_cuda_fv_step_euler_3d_f64(const double* q_in, double* q_out, int64_t n_patches, int patch_size, int halo,
+                                      int n_aux, double dt, double* lambda_patch, double* lambda_max,
+                                      unsigned flags, void* stream);
+int exahype_cuda_fv_step_swe_2d_f64(const double* q_in, double* q_out, int64_t n_patches, int patch_size, int halo,
+                                    int n_aux, double dt, double* lambda_patch, double* lambda_max,
+                                    unsigned flags, void* stream);
+int exahype_cuda_fv_step_swe_2d_f32(const float* q_in, float* q_out, int64_t n_patches, int patch_size, int halo,
+                                    int n_aux, float dt, float* lambda_patch, float* lambda_max,
+                                    unsigned flags, void* stream);
+
+/*
+ * The reference's own call shape, `time_step(Q, dt)` on HOST memory (reference Unit test/correctness_test.cpp:195):
+ * copies the batch to the device in chunks, updates it there and copies the interior back, with copies and kernels
+ * overlapped on internal streams.  q_host is updated in place (haloed) or q_out_host receives the result
+ * (layout per flags; may equal q_host when haloed).  lambda_max_host (nullable) receives the batch maximum.
+ * Pinned host memory gives full PCIe bandwidth; pageable memory works.  Synchronous: returns when done.
+ */
+int exahype_cuda_time_step_host(const exahype_fv_config* cfg, const void* q_host, void* q_out_host,
+                                int64_t n_patches, double dt, void* lambda_patch_host, void* lambda_max_host);
+/* Releases the staging buffers and streams cached by exahype_cuda_time_step_host for the current device. */
+int exahype_cuda_host_pipeline_release(void);
+/* Chunk size (patches) and number of in-flight chunks used by exahype_cuda_time_step_host; 0 keeps the default. */
+int exahype_cuda_host_pipeline_configure(int64_t chunk_patches, int depth);
+
+/* Number of kernels launched by this library in this process since load (for bench.py's gpu_launches). */
+int64_t exahype_cuda_launch_count(void);
+/* Kernel geometry picked for cfg on the current device: grid, block, dynamic smem bytes, patches per tile. */
+int exahype_cuda_fv_launch_info(const exahype_fv_config* cfg, int64_t n_patches, int* grid, int* block,
+                                int* smem_bytes, int* patches_per_tile);
+
+/*
+ * Global admissible time step across GPUs: one NCCL all-reduce(max) of a single scalar
+ * (new; the reference has no distributed code).  One communicator per process/GPU.
+ *   exahype_cuda_nccl_unique_id  writes a 128-byte ncclUniqueId (rank 0 creates it, the host plumbing broadcasts it)
+ *   exahype_cuda_comm_init       ncclCommInitRank on the current device; *comm receives an opaque handle
+ *   exahype_cuda_allreduce_max   in-place max over ranks of count values of dtype at device pointer `values`
+ */
+int exahype_cuda_nccl_unique_id(void* id128);
+int exahype_cuda_comm_init(void** comm, const void* id128, int world_size, int rank);
+int exahype_cuda_comm_destroy(void* comm);
+int exahype_cuda_allreduce_max(void* comm, void* values, int64_t count, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXAHYPE_CUDA_H */

@@ -1,0 +1,277 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- bit-exact in fp64 and fp32.
+
+The oracle reproduces the reference's compiled kernel bit for bit (tests/test_oracle_golden.py), so equality with
+the oracle is equality with the reference's arithmetic.  The stated contract (BASELINE.json north_star) is 1e-12
+relative in fp64; these tests hold the stronger property, and `TOL` below is only used where a looser
+statement is the point (fp32 against fp64).
+"""
+import dataclasses
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP64 = 1e-12          # the north-star bound; the tests assert bitwise equality, which implies it
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from exahype_b200 import runtime
+    assert runtime.device_count() >= 1
+    return runtime
+
+
+def gpu_step(torch, upd, q_np, dt, out=None, want_lambda=True):
+    """Runs one step on the device; returns (q_out numpy, lambda_patch numpy, lambda_max)."""
+    tdt = torch.float64 if upd.dtype == "f64" else torch.float32
+    q = torch.from_numpy(q_np).cuda()
+    n = q_np.shape[0]
+    lam = torch.full((n,), -1.0, dtype=tdt, device="cuda")
+    lmax = torch.full((1,), -1.0, dtype=tdt, device="cuda")
+    if upd.output == "unhaloed":
+        out = torch.full(upd.out_shape(n), 7.0, dtype=tdt, device="cuda")
+    res = upd.step(q, out, dt, lam if want_lambda else None, lmax if want_lambda else None)
+    torch.cuda.synchronize()
+    return res.cpu().numpy(), lam.cpu().numpy(), float(lmax.item())
+
+
+def oracle_cfg(oracle, upd):
+    return oracle.OracleConfig(dim=upd.dim, patch_size=upd.patch_size, halo=upd.halo_size, n_real=upd.n_real,
+                               n_aux=upd.n_aux, model=oracle.MODEL_EULER if upd.model == "euler" else oracle.MODEL_SWE,
+                               diss=oracle.DISS_ALL if upd.dissipation == "all" else oracle.DISS_VAR0)
+
+
+def interior(upd, a):
+    h = upd.halo_size
+    sl = (slice(None),) + (slice(h, -h),) * upd.dim
+    return a[sl]
+
+
+def assert_bitwise(a, b, what=""):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    same = a.view(np.uint8) == b.view(np.uint8)
+    if not same.all():
+        bad = np.argwhere(a != b)
+        rel = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+        raise AssertionError(f"{what}: {len(bad)} values differ, first at {bad[0]}, max rel diff {rel:.3e}")
+
+
+# ----------------------------------------------------------------------------------------- goldens
+@pytest.mark.parametrize("diss", ["var0", "all"])
+@pytest.mark.parametrize("dt", [1.0, 0.01])
+def test_config_c1_sin_input_golden_g1(torch, rt, oracle, diss, dt):
+    """BASELINE config C1: 2-D Euler 3x3+1, 1000 patches (ragged last tile: 1000 = 35*28 + 20)."""
+    upd = rt.PatchUpdate("euler", 2, 3, 1, 4, 0, dissipation=diss)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_sin(cfg, 1000)
+    want = q0.copy()
+    lam_o, lmax_o = oracle.step(cfg, want, dt)
+    got, lam, lmax = gpu_step(torch, upd, q0, dt)
+    assert_bitwise(got, want, "C1")
+    assert_bitwise(lam, lam_o, "lambda_patch")
+    assert lmax == lmax_o == 1.1326339818690889
+    expected = {("var0", 1.0): "1334ede917c43f96", ("all", 1.0): "aa5c6cb6b3c1c18e",
+                ("var0", 0.01): "fbacf0e93e60875b", ("all", 0.01): "369e22f97aff515c"}[(diss, dt)]
+    assert oracle.fnv1a64(got) == expected
+
+
+def test_reference_kernel_shape_g0(torch, rt, oracle):
+    """Shape of the reference's committed kernel (2-D, 4x4+1, 5+5 variables).  The committed file's transposed
+    ranges read uninitialised rows; on the cells those rows cannot reach, the CUDA result equals the output of the
+    reference's own compiled kernel bit for bit (fixture written by tests/golden/make_golden.py)."""
+    upd = rt.PatchUpdate("euler", 2, 4, 1, 5, 5)
+    cfg = oracle_cfg(oracle, upd)
+    with open(os.path.join(HERE, "golden", "g0_reference_kernel.json")) as f:
+        g0 = json.load(f)
+    bits = lambda hx: np.array([int(h, 16) for h in hx], dtype=np.uint64).view(np.float64)
+    q0 = bits(g0["input"]).reshape(1, 6, 6, 10).copy()
+    ref_out = bits(g0["output"]).reshape(1, 6, 6, 10)
+    got, lam, lmax = gpu_step(torch, upd, q0, g0["dt"])
+    assert_bitwise(got[0, 2:4, 2:4], ref_out[0, 2:4, 2:4], "inner cells vs compiled reference")
+    assert_bitwise(got[..., 5:], q0[..., 5:], "aux pass through")
+    want = q0.copy(); oracle.step(cfg, want, g0["dt"])
+    assert_bitwise(got, want, "G0h")
+    assert oracle.fnv1a64(got) == "5c1d83d32c1d0f28"
+
+
+@pytest.mark.parametrize("diss,fill,expected", [("var0", "sin", "53201509629d2991"), ("all", "sin", "78219e9b15eba6f7"),
+                                                ("var0", "syn", "f8486ef10dfe78d6"), ("all", "syn", "c72ba3f4ebf895ec")])
+def test_euler3d_goldens_g3(torch, rt, oracle, diss, fill, expected):
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0, dissipation=diss)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_sin(cfg, 4) if fill == "sin" else oracle.fill_synthetic(cfg, 4)
+    want = q0.copy(); lam_o, lmax_o = oracle.step(cfg, want, 0.01)
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.01)
+    assert_bitwise(got, want, "G3")
+    assert oracle.fnv1a64(got) == expected
+    assert_bitwise(lam, lam_o, "lambda")
+    assert lmax == lmax_o
+    np.testing.assert_allclose(got, want, rtol=TOL_FP64, atol=0)
+
+
+@pytest.mark.parametrize("diss,expected", [("var0", "1856adbc23fec8cd"), ("all", "8e53779668580e14")])
+def test_euler2d_golden_g2r(torch, rt, oracle, diss, expected):
+    upd = rt.PatchUpdate("euler", 2, 16, 1, 4, 0, dissipation=diss)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, 8)
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.01)
+    assert oracle.fnv1a64(got) == expected
+    assert lmax == 2.1332213875447144
+
+
+# ----------------------------------------------------------------------------------------- every committed shape
+def _committed():
+    from exahype_b200 import runtime
+    return [(i["model"], i["dim"], i["patch_size"], i["halo_size"], i["n_real"], i["n_aux"], i["dtype"])
+            for i in runtime.committed_instantiations()]
+
+
+@pytest.mark.parametrize("shape", _committed(), ids=lambda s: "-".join(map(str, s)))
+@pytest.mark.parametrize("diss", ["var0", "all"])
+@pytest.mark.parametrize("output", ["haloed", "unhaloed"])
+def test_every_instantiation_matches_oracle_bitwise(torch, rt, oracle, shape, diss, output):
+    model, dim, P, h, nr, na, dtype = shape
+    upd = rt.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output)
+    cfg = oracle_cfg(oracle, upd)
+    npdt = np.float64 if dtype == "f64" else np.float32
+    info = upd.launch_info(10 ** 6)
+    n = 3 * info["patches_per_tile"] * 5 + 1          # several tiles per CTA is not needed for parity; ragged tail is
+    q0 = oracle.fill_synthetic(cfg, n, dtype=npdt)
+    want = q0.copy()
+    lam_o, lmax_o = oracle.step(cfg, want, 0.01, nthreads=4)
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.01)
+    if output == "haloed":
+        assert_bitwise(got, want, "haloed")
+    else:
+        assert got.shape == upd.out_shape(n)
+        assert_bitwise(got, interior(upd, want), "unhaloed")
+    assert_bitwise(lam, lam_o, "lambda_patch")
+    assert lmax == float(lmax_o)
+
+
+def test_fp32_error_bound_against_fp64_oracle(torch, rt, oracle):
+    """Stated fp32 bound: max |q32 - q64| <= 2e-6 * max|q64| per variable on the synthetic SWE and Euler states."""
+    for model, dim, P, nr, na in (("swe", 2, 32, 3, 1), ("euler", 3, 8, 5, 0), ("euler", 2, 16, 4, 0)):
+        upd32 = rt.PatchUpdate(model, dim, P, 1, nr, na, dtype="f32", dissipation="all")
+        cfg = oracle_cfg(oracle, upd32)
+        q64 = oracle.fill_synthetic(cfg, 64)
+        q32 = q64.astype(np.float32)
+        oracle.step(cfg, q64, 0.01, nthreads=4)
+        got, _, _ = gpu_step(torch, upd32, q32, 0.01)
+        scale = np.abs(q64).reshape(-1, nr + na).max(axis=0)
+        err = np.abs(got.astype(np.float64) - q64).reshape(-1, nr + na).max(axis=0)
+        assert (err <= 2e-6 * scale).all(), (model, err / scale)
+
+
+# ----------------------------------------------------------------------------------------- semantics of the boundary
+def test_out_of_place_haloed_writes_interior_only(torch, rt, oracle):
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, 37)
+    q = torch.from_numpy(q0).cuda()
+    out = torch.full_like(q, -123.0)
+    upd.step(q, out, 0.01)
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    assert_bitwise(q.cpu().numpy(), q0, "input untouched")
+    want = q0.copy(); oracle.step(cfg, want, 0.01)
+    assert_bitwise(interior(upd, out), interior(upd, want), "interior")
+    mask = np.ones(out.shape, bool); mask[:, 1:-1, 1:-1, 1:-1] = False
+    assert (out[mask] == -123.0).all()
+
+
+def test_lambda_accumulates_across_launches_and_empty_batch(torch, rt, oracle):
+    upd = rt.PatchUpdate("euler", 2, 16, 1, 4, 0)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, 64)
+    lam_o, lmax_o = oracle.step(cfg, q0.copy(), 0.01)
+    q = torch.from_numpy(q0).cuda()
+    lmax = torch.zeros(1, dtype=torch.float64, device="cuda")
+    half = q0.shape[0] // 2
+    upd.step(q[:half].clone(), None, 0.01, None, lmax)
+    upd.step(q[half:].clone(), None, 0.01, None, lmax, accumulate_lambda=True)
+    assert float(lmax.item()) == lmax_o
+    upd.step(q[:0], None, 0.01, None, lmax)          # zero patches: resets lambda_max, launches nothing
+    assert float(lmax.item()) == 0.0
+
+
+def test_host_time_step_equals_device_step(torch, rt, oracle):
+    """The reference's call shape time_step(Q, dt) on host memory, chunked so several pipeline slots are used."""
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, 301)
+    want = q0.copy(); lam_o, lmax_o = oracle.step(cfg, want, 0.01, nthreads=4)
+    rt.load().exahype_cuda_host_pipeline_configure(64, 3)
+    try:
+        Q = q0.copy()
+        lam = np.zeros(301)
+        lmax = upd.time_step(Q, 0.01, lambda_patch=lam)
+        assert_bitwise(Q, want, "host in place")
+        assert_bitwise(lam, lam_o, "host lambda")
+        assert lmax == lmax_o
+        upd_u = dataclasses.replace(upd, output="unhaloed")
+        out = np.zeros(upd_u.out_shape(301))
+        upd_u.time_step(q0.copy(), 0.01, Q_out=out)
+        assert_bitwise(out, interior(upd, want), "host unhaloed")
+        pinned = torch.from_numpy(q0.copy()).pin_memory()
+        upd.time_step(pinned.numpy(), 0.01)
+        assert_bitwise(pinned.numpy(), want, "pinned")
+    finally:
+        rt.load().exahype_cuda_host_pipeline_configure(0, 3)
+        rt.load().exahype_cuda_host_pipeline_release()
+
+
+def test_errors_on_device(torch, rt):
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0)
+    q = torch.zeros(upd.in_shape(2), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        upd.step(q.float(), None, 0.1)
+    with pytest.raises(ValueError):
+        upd.step(torch.zeros(17, dtype=torch.float64, device="cuda"), None, 0.1)
+    with pytest.raises(rt.ExaHyPECudaError) as e:
+        rt.PatchUpdate("euler", 3, 7, 1, 5, 0).step(torch.zeros((1, 9, 9, 9, 5), dtype=torch.float64, device="cuda"), None, 0.1)
+    assert e.value.code == -2
+    before = rt.launch_count()
+    upd.step(q + 1.0, None, 0.1)
+    torch.cuda.synchronize()
+    assert rt.launch_count() == before + 1
+
+
+# ----------------------------------------------------------------------------------------- BASELINE sizes
+@pytest.mark.parametrize("model,dim,P,nr,na,n", [("euler", 3, 8, 5, 0, 32768), ("euler", 2, 16, 4, 0, 65536)])
+def test_full_size_properties(torch, rt, oracle, model, dim, P, nr, na, n):
+    """At the full BASELINE batch sizes: determinism, shard-independence (what multi-GPU relies on), untouched
+    halos, lambda_max == max(lambda_patch), and bitwise parity on the first / last / middle patches."""
+    upd = rt.PatchUpdate(model, dim, P, 1, nr, na)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, n)
+    q = torch.from_numpy(q0).cuda()
+    lam = torch.zeros(n, dtype=torch.float64, device="cuda")
+    lmax = torch.zeros(1, dtype=torch.float64, device="cuda")
+    a = q.clone(); upd.step(a, None, 0.01, lam, lmax)
+    b = q.clone(); upd.step(b, None, 0.01)
+    assert torch.equal(a, b)
+    # two shards processed separately == the whole batch
+    c = q.clone(); cut = n // 2 + 3
+    upd.step(c[:cut], None, 0.01); upd.step(c[cut:], None, 0.01)
+    assert torch.equal(a, c)
+    assert float(lmax.item()) == float(lam.max().item())
+    a_np = a.cpu().numpy()
+    mask = np.ones(a_np.shape[1:], bool); mask[(slice(1, -1),) * dim] = False
+    assert_bitwise(a_np[:, mask], q0[:, mask], "halos")
+    for lo in (0, n // 2 - 32, n - 64):
+        want = q0[lo:lo + 64].copy()
+        lam_o, _ = oracle.step(cfg, want, 0.01, nthreads=4)
+        assert_bitwise(a_np[lo:lo + 64], want, f"patches {lo}..")
+        assert_bitwise(lam[lo:lo + 64].cpu().numpy(), lam_o, "lambda")

@@ -1,0 +1,150 @@
+"""Back-end printers: CPPPrinter output compiles and equals the oracle bit for bit (CPU); CUDAPrinter recognises the
+program, emits the expected functors and its unit cross-compiles for sm_100a (no GPU needed for that)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden import batched_stateless  # noqa: E402
+
+from exahype import KernelBuilder  # noqa: E402
+from exahype.printers import CPPPrinter, CUDAPrinter, MLIRPrinter  # noqa: E402
+from exahype_b200.printers import UnsupportedKernel, analyse  # noqa: E402
+
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def compile_cpp(tmp_path, kernel, dims):
+    src = tmp_path / "generated.cpp"
+    CPPPrinter(kernel).file(str(src), header_file_name="Functions.h")
+    lib = tmp_path / "libgenerated.so"
+    subprocess.run([GXX, "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", f"-DDIMENSIONS={dims}",
+                    "-I", os.path.join(HERE, "data"), str(src), os.path.join(HERE, "data", "Functions.cpp"),
+                    "-o", str(lib)], check=True)
+    fn = getattr(ctypes.CDLL(str(lib)), "_Z9time_stepPdd")     # C++ linkage, like the reference's test.h:3
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    fn.restype = None
+    return fn
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 1, 4, 0, 7), (2, 4, 1, 4, 2, 3), (3, 4, 1, 5, 0, 2), (2, 5, 2, 4, 0, 2)])
+def test_cpp_printer_output_equals_oracle(tmp_path, oracle, shape):
+    dim, P, h, nr, na, B = shape
+    time_step = compile_cpp(tmp_path, batched_stateless(KernelBuilder, dim, P, h, nr, na, B), dim)
+    cfg = oracle.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na)
+    q = oracle.fill_synthetic(cfg, B)
+    want = q.copy()
+    oracle.step(cfg, want, 0.01)
+    time_step(q.ctypes.data, 0.01)
+    assert np.array_equal(q, want)
+
+
+def test_cpp_printer_signature_and_ranges():
+    code = CPPPrinter(batched_stateless(KernelBuilder, 2, 4, 1, 5, 5)).code
+    assert code.startswith("void time_step(double* Q, double dt) {")
+    assert "new double[360]()" in code and "new double[36]()" in code
+    assert "Flux(&Q_copy[360*patch + 60*i + 10*j], normal, &tmp_flux_x[180*patch + 30*i + 5*j]);" in code
+    # flux sweep along i: full range on i, interior on j (reference CPPPrinter.py:132-137; committed file has it transposed)
+    flux_x = code[code.index("normal = 0;"):code.index("normal = 1;")]
+    assert "int i = 0; i < 6" in flux_x and "int j = 1; j < 5" in flux_x
+    assert "&&" not in code and "None" not in code and "patch - 1" not in code
+    with pytest.raises(NotImplementedError):
+        MLIRPrinter(batched_stateless(KernelBuilder, 2, 4, 1, 5, 5))
+
+
+def test_cuda_printer_recognises_the_program():
+    k = batched_stateless(KernelBuilder, 3, 8, 1, 5, 0, 4)
+    prog = analyse(k)
+    assert (prog.q_in, prog.q_work, prog.flux_tmp, prog.eigen_tmp) == ("Q", "Q_copy", "tmp_flux", "tmp_eigen")
+    assert (prog.flux_fn, prog.eigen_fn, prog.max_fn, prog.dt) == ("Flux", "maxEigenvalue", "max", "dt")
+    assert prog.normals == [0, 1, 2]
+    assert prog.flux_update == "qc - T(0.5)*f_plus + T(0.5)*f_minus"
+    assert prog.dissipation == ("T(0.5)*dt*((-q_plus + q0)*::exahype::fv_max(l_plus, l0) + "
+                                "(q_minus - q0)*::exahype::fv_max(l_minus, l0)) + qc")
+    assert prog.dissipation_all is False            # tmp_eigen silences the var loop, as in the reference's output
+    p = CUDAPrinter(k, model="euler")
+    assert "using Physics = ::exahype::EulerPhysics<3, 5, 0>;" in p.code
+    assert 'extern "C"' in p.code and "int time_step(const void* q_in" in p.code
+    assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true>" in p.code
+    assert CUDAPrinter(k, function_name="step32", dtype="f32", dissipation="all", model="euler").code.count("float") >= 2
+
+
+def test_cuda_printer_rejects_other_programs():
+    k = KernelBuilder(2, 4, 1, 4, 0)
+    q, qc = k.item("Q"), k.item("Q_copy")
+    k.directional_item("tmp_flux"); k.directional_item("tmp_eigen", struct=False)
+    k.single(qc[0], q[0]); k.single(q[0], qc[0])
+    with pytest.raises(UnsupportedKernel):
+        CUDAPrinter(k)
+    with pytest.raises(UnsupportedKernel):
+        CUDAPrinter(batched_stateless(KernelBuilder, 2, 4, 0, 4, 0))   # no halo layer to read
+
+
+def _swe_kernel():
+    """Shallow water declared with SymPy bodies: the CUDA functors are generated, not hand-written."""
+    import sympy
+    from sympy.codegen.ast import real, integer, none
+    k = KernelBuilder(dim=2, patch_size=16, halo_size=1, n_real=3, n_aux=1)
+    Q, Qc = k.item('Q'), k.item('Q_copy')
+    F, L = k.directional_item('tmp_flux'), k.directional_item('tmp_eigen', struct=False)
+    dt = k.const('dt'); normal = k.directional_const('normal', [0, 1])
+    g = 9.81
+
+    def flux(q, n):
+        un = q[n + 1] / q[0]
+        f = [un * q[0], un * q[1], un * q[2]]
+        f[n + 1] = f[n + 1] + 0.5 * g * q[0] * q[0]
+        return f
+
+    def eig(q, n):
+        un, c = q[n + 1] / sympy.Abs(q[0]), sympy.sqrt(g * sympy.Abs(q[0]))
+        return sympy.Max(sympy.Abs(un - c), sympy.Abs(un + c))
+    Flux = k.function('Flux', parameter_types=[Q, real, Q], return_type=integer, body=flux)
+    Eig = k.function('maxEigenvalue', parameter_types=[Q, real], return_type=real, body=eig)
+    Max = k.function('max', parameter_types=[Q, Q], return_type=none)
+    k.single(Qc[0], Q[0])
+    k.directional(Flux(Qc[0], normal, F[0]))
+    k.directional(L[0], Eig(Qc[0], normal))
+    k.directional(Qc[0], Qc[0] + 0.5 * (F[-1] - F[1]))
+    left = -Max(L[-1], L[0]) * (Q[0] - Q[-1]); right = -Max(L[1], L[0]) * (Q[0] - Q[1])
+    k.directional(Qc[0], Qc[0] + 0.5 * dt * (left - right), struct=True)
+    k.single(Q[0], Qc[0])
+    return k
+
+
+def test_generated_units_cross_compile_for_sm100a(tmp_path):
+    """nvcc -gencode arch=compute_100a,code=sm_100a on generated units: hand-written family, SymPy bodies, and the
+    user's own device source with the reference's Functions.h signatures."""
+    lib = CUDAPrinter(_swe_kernel(), function_name="swe_step").build(directory=str(tmp_path))
+    assert os.path.exists(lib.lib_path) and lib.in_shape(2) == (2, 18, 18, 4)
+    assert "F[1] = " in CUDAPrinter(_swe_kernel()).code
+
+    k = batched_stateless(KernelBuilder, 2, 8, 1, 4, 0)
+    hdr = tmp_path / "Functions.cuh"
+    hdr.write_text('''
+template <class T> __device__ void Flux(const T* Q, int normal, T* F) {
+  const T irho = T(1.0) / Q[0];
+  const T p = (T(1.4) - 1) * (Q[3] - T(0.5) * irho * (Q[1] * Q[1] + Q[2] * Q[2]));
+  const T coeff = irho * Q[normal + 1];
+  F[0] = coeff * Q[0]; F[1] = coeff * Q[1]; F[2] = coeff * Q[2]; F[3] = coeff * Q[3] + coeff * p;
+  F[normal + 1] += p;
+}
+template <class T> __device__ T maxEigenvalue(const T* Q, int normal) {
+  const T irho = T(1.0) / fabs(Q[0]);
+  const T p = (T(1.4) - 1) * (Q[3] - T(0.5) * irho * (Q[1] * Q[1] + Q[2] * Q[2]));
+  const T c = sqrt(T(1.4) * fabs(p) * irho);
+  const T u = Q[normal + 1] * irho;
+  return fmax(fabs(u - c), fabs(u + c));
+}
+''')
+    printer = CUDAPrinter(k, function_name="user_step")
+    src = tmp_path / "user_step.cu"
+    printer.file(str(src), header_file_name="Functions.cuh")
+    assert src.read_text().startswith('#include "Functions.cuh"')
+    built = printer.build(directory=str(tmp_path), include_dirs=[str(tmp_path)])
+    assert os.path.exists(built.lib_path)
