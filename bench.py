@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the batched stateless FV Rusanov patch update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c4|c4f32|c1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over the whole batch: fused patch-update kernel (+ the NCCL all-reduce(max) of
+the admissible-time-step scalar when N > 1).  Prints ONE JSON line on rank 0.
+
+  value     patch-cell updates/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the reference-facing host call exahype_cuda_time_step_host(Q_host, dt): pinned host
+            buffers, H2D and D2H inside the timed region
+  roofline  algorithmic bytes / average kernel duration vs the measured HBM copy peak
+  cpu_baseline  the CPU oracle (port of the reference kernel's arithmetic) on this box's host cores, bounded sample
+
+Weak scaling: every rank owns `batch` patches (contiguous shard of the global batch, counter-based synthetic input).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, dim, P, halo, n_real, n_aux, dtype, patches per GPU, description)
+    "c3": ("euler", 3, 8, 1, 5, 0, "f64", 32768, "3D Euler (5 unknowns) Rusanov FV, 8x8x8 patches + 1 halo, batch of 32,768 patches, fp64"),
+    "c2": ("euler", 2, 16, 1, 4, 0, "f64", 65536, "2D Euler Rusanov FV, 16x16 patches + 1 halo, batch of 65,536 patches, fp64"),
+    "c4": ("swe", 2, 32, 1, 3, 1, "f64", 65536, "2D shallow-water (3 unknowns + bathymetry) Rusanov FV, 32x32 patches, batch of 65,536, fp64"),
+    "c4f32": ("swe", 2, 32, 1, 3, 1, "f32", 65536, "2D shallow-water Rusanov FV, 32x32 patches, batch of 65,536, fp32"),
+    "c1": ("euler", 2, 3, 1, 4, 0, "f64", 1000, "2D Euler (4 unknowns) Rusanov FV, 3x3 patches + 1 halo, batch of 1,000 patches, fp64"),
+}
+METRIC = "patch_cell_updates_per_sec"
+UNIT = "cell-updates/s"
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_rate(workload: str, min_seconds: float, sample_patches: int):
+    """Times the CPU oracle (contraction-free -O3 build, OpenMP over patches: all host threads) on a bounded sample of
+    the workload.  Returns (cell-updates/s, description dict)."""
+    import numpy as np
+    import oracle as O
+    model, dim, P, h, nr, na, dtype, _, _ = WORKLOADS[workload]
+    cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
+                         model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
+    threads = O.max_threads()
+    npdt = np.float64 if dtype == "f64" else np.float32
+    q0 = O.fill_synthetic(cfg, sample_patches, dtype=npdt)
+    q = q0.copy()
+    O.step(cfg, q, 0.01, nthreads=threads, fast=True)          # warm-up (page faults, thread pool)
+    passes, elapsed, t0 = 0, 0.0, time.perf_counter()
+    while time.perf_counter() - t0 < min_seconds or passes < 3:
+        np.copyto(q, q0)                                        # restore outside the timed region: the state stays admissible
+        t1 = time.perf_counter()
+        O.step(cfg, q, 0.01, nthreads=threads, fast=True)
+        elapsed += time.perf_counter() - t1
+        passes += 1
+    cells = sample_patches * P ** dim * passes
+    return cells / elapsed, {"cores": threads, "kind": "port",
+                             "sample": f"{sample_patches} patches of the workload x {passes} passes "
+                                       f"({elapsed:.1f} s), OpenMP over patches, gcc -O3 -march=native -ffp-contract=off"}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference kernel's arithmetic on the host CPU (the oracle port; the reference's own
+    compiled kernel, oracle/_ref, is hard-wired to one 4x4 2-D patch and cannot run this workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, dim, P, h, nr, na, dtype, batch, desc = WORKLOADS[args.workload]
+    import numpy as np
+    import oracle as O
+    cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
+                         model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
+    threads = O.max_threads()
+    sample = min(batch, args.cpu_sample)
+    npdt = np.float64 if dtype == "f64" else np.float32
+    q0 = O.fill_synthetic(cfg, sample, dtype=npdt)
+    q = q0.copy()
+    for _ in range(max(1, args.warmup)):
+        np.copyto(q, q0)
+        O.step(cfg, q, 0.01, nthreads=threads, fast=True)
+    elapsed = 0.0
+    for _ in range(args.steps):
+        np.copyto(q, q0)                                        # restore (untimed) so every step sees admissible data
+        t0 = time.perf_counter()
+        O.step(cfg, q, 0.01, nthreads=threads, fast=True)
+        elapsed += time.perf_counter() - t0
+    value = sample * P ** dim * args.steps / elapsed
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": desc, "patches_per_step": sample, "note": "bounded sample of the workload per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} patches per step x {args.steps} steps, OpenMP over patches"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="patches per GPU (default: the workload's BASELINE batch)")
+    ap.add_argument("--output", default="unhaloed", choices=["unhaloed", "haloed"])
+    ap.add_argument("--dissipation", default="var0", choices=["var0", "all"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variants", action="store_true", help="also time the other output/dissipation variants and workloads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from exahype_b200 import runtime
+    from exahype_b200.dist import PatchSharding, TimestepReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world and rank == 0:
+        print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    model, dim, P, h, nr, na, dtype, batch, desc = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=args.dissipation, output=args.output)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    npdt = np.float64 if dtype == "f64" else np.float32
+    shard = PatchSharding(global_patches=batch * world, world_size=world, rank=rank)
+    assert shard.count == batch
+
+    # synthetic admissible input of SURVEY.md 8d, generated on the device shard by shard (same bits as the oracle's)
+    q_in = synthetic_on_device(torch, upd, shard.first, batch, tdt)
+    q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
+    lam_patch = torch.empty(batch, dtype=tdt, device="cuda")
+    lam_max = torch.zeros(1, dtype=tdt, device="cuda")
+    reducer = TimestepReducer(world, rank) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+        if reducer is not None:
+            reducer.allreduce_max(lam_max)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    launches0 = runtime.launch_count()
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for i in range(args.steps):
+        k_start[i].record(stream)
+        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+        k_stop[i].record(stream)
+        if reducer is not None:
+            reducer.allreduce_max(lam_max)
+    t_end.record(stream)
+    barrier()
+    launches = runtime.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(k_start, k_stop))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kernel_ms = t.tolist()
+    cells_per_step = batch * world * P ** dim
+    value = cells_per_step * args.steps / (elapsed_ms * 1e-3)
+    lam_global = float(lam_max.item())
+
+    # --- end to end through the host-facing C-ABI call (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(upd.in_shape(batch), dtype=tdt).pin_memory()
+        host_in.copy_(q_in)
+        host_out = torch.empty(upd.out_shape(batch), dtype=tdt).pin_memory()
+        upd.time_step(host_in.numpy(), 0.01, Q_out=host_out.numpy())            # warm-up: allocates the staging ring
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            lam_e2e = upd.time_step(host_in.numpy(), 0.01, Q_out=host_out.numpy())
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        es = 8 if dtype == "f64" else 4
+        e2e = {"value": cells_per_step * args.e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(host_in.numel() * es) * world,
+               "d2h_bytes_per_step": int(host_out.numel() * es + es) * world,
+               "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
+               "api": "exahype_cuda_time_step_host (chunked H2D -> kernel -> D2H over 3 stream slots)",
+               "lambda_max_matches_device": bool(float(lam_e2e) == float(lam_patch.max().item()))}
+        del host_in, host_out
+        runtime.load().exahype_cuda_host_pipeline_release()
+
+    variants = None
+    if args.variants and world == 1:
+        variants = time_variants(torch, runtime, args)
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        alg_bytes = upd.algorithmic_bytes_per_patch * batch          # per launch (= per GPU)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        info = upd.launch_info(batch)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": desc, "patches_per_gpu": batch, "global_patches": batch * world,
+                       "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)",
+                       "parallelism": f"patch-sharded x{world}" + (", NCCL allreduce-max of lambda per step" if world > 1 else ""),
+                       "l2": "inputs larger than L2: %.2f GB read + %.2f GB written per step per GPU"
+                             % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
+                       "kernel": info},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                         "frac_of_8TBs_nominal": achieved / 8000.0},
+            "hbm_gbs_aggregate": achieved * world,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "lambda_max": lam_global,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if variants is not None:
+            line["variants"] = variants
+        if not args.no_cpu and world >= 1:
+            cpu_value, cpu_desc = cpu_reference_rate(args.workload, args.cpu_seconds, min(batch, args.cpu_sample))
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, **cpu_desc}
+        print(json.dumps(line), flush=True)
+
+    if reducer is not None:
+        reducer.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def synthetic_on_device(torch, upd, first_patch: int, n_patches: int, tdt, device="cuda"):
+    """SplitMix64-based admissible state of SURVEY.md 8d, evaluated with torch integer ops on the device so a 1.3 GB
+    shard does not cross PCIe.  Bit-identical to oracle.fill_synthetic (tests/test_bench_input.py)."""
+    nv = upd.n_var
+    cells = n_patches * upd.side ** upd.dim
+    first_cell = first_patch * upd.side ** upd.dim
+    out = torch.empty((cells, nv), dtype=torch.float64, device=device)
+    chunk = 1 << 22
+    mask = (1 << 64) - 1
+
+    def c(x):  # two's-complement int64 constant
+        x &= mask
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def lsr(z, s):  # logical shift right on int64
+        return (z >> s) & c((1 << (64 - s)) - 1)
+
+    for lo in range(0, cells, chunk):
+        n = min(chunk, cells - lo)
+        idx = (torch.arange(n, dtype=torch.int64, device=device).unsqueeze(1) + (first_cell + lo)) * nv \
+            + torch.arange(nv, dtype=torch.int64, device=device).unsqueeze(0)
+        z = (idx + 20240601) * c(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        u = lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
+        o = out[lo:lo + n]
+        if upd.model == "euler":
+            d = upd.dim
+            rho = 1.0 + u[:, 0]
+            ke = torch.zeros_like(rho)
+            for k in range(d):
+                vel = u[:, 1 + k] - 0.5
+                o[:, 1 + k] = rho * vel
+                ke = ke + vel * vel
+            p = 1.0 + u[:, d + 1]
+            o[:, 0] = rho
+            o[:, d + 1] = p / (1.4 - 1.0) + 0.5 * rho * ke
+            o[:, d + 2:] = u[:, d + 2:]
+        else:
+            hgt = 1.0 + u[:, 0]
+            o[:, 0] = hgt
+            o[:, 1] = hgt * (0.2 * (u[:, 1] - 0.5))
+            o[:, 2] = hgt * (0.2 * (u[:, 2] - 0.5))
+            o[:, 3:] = 0.1 * u[:, 3:]
+    return out.to(tdt).reshape(upd.in_shape(n_patches))
+
+
+def time_variants(torch, runtime, args):
+    """Kernel-only timings of the other committed variants / workloads (informative; same timing hygiene)."""
+    import numpy as np
+    res = {}
+    for wl in ("c3", "c2", "c4", "c4f32", "c1"):
+        model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        for output in ("unhaloed", "haloed"):
+            for diss in ("var0", "all"):
+                upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output)
+                q_in = synthetic_on_device(torch, upd, 0, batch, tdt)
+                q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
+                lam = torch.zeros(1, dtype=tdt, device="cuda")
+                for _ in range(3):
+                    upd.step(q_in, q_out, 0.01, None, lam)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(10):
+                    upd.step(q_in, q_out, 0.01, None, lam)
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 10
+                gbs = upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9
+                res[f"{wl}/{output}/{diss}"] = {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
+                                                "algorithmic_GBs": gbs}
+                del q_in, q_out
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,51 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
   }
 }
 
+
+/* Cell lists, built once per call: the loop ranges of the generated kernel as index sets. */
+typedef struct {
+  int* sweep[FVO_MAX_DIM];   /* cells of the flux/eigen sweep of axis n, in loop order */
+  int n_sweep[FVO_MAX_DIM];
+  int* interior;             /* interior cells, in loop order */
+  int n_interior;
+} fvo_cells;
+
+static int fvo_is_interior(const fvo_geom* g, int cell, int skip_axis) {
+  for (int m = 0; m < g->dim; ++m) {
+    if (m == skip_axis) continue;
+    const int cm = (cell / g->stride[m]) % g->S;
+    if (cm < g->h || cm >= g->P + g->h) return 0;
+  }
+  return 1;
+}
+
+/* HEAD: full along n, interior across (CPPPrinter.py:132-137); COMMITTED: transposed (test.cpp:22-23) */
+static int fvo_in_sweep(const fvo_geom* g, int ranges, int cell, int n) {
+  if (ranges == FVO_RANGES_HEAD) return fvo_is_interior(g, cell, n);
+  const int cn = (cell / g->stride[n]) % g->S;
+  return cn >= g->h && cn < g->P + g->h;
+}
+
+static void fvo_free_cells(fvo_cells* c) {
+  for (int n = 0; n < FVO_MAX_DIM; ++n) free(c->sweep[n]);
+  free(c->interior);
+}
+
+static int fvo_make_cells(const fvo_geom* g, int ranges, fvo_cells* c) {
+  memset(c, 0, sizeof *c);
+  c->interior = (int*)malloc(sizeof(int) * (size_t)g->ncell);
+  if (!c->interior) return -1;
+  for (int cell = 0; cell < g->ncell; ++cell)
+    if (fvo_is_interior(g, cell, -1)) c->interior[c->n_interior++] = cell;
+  for (int n = 0; n < g->dim; ++n) {
+    c->sweep[n] = (int*)malloc(sizeof(int) * (size_t)g->ncell);
+    if (!c->sweep[n]) { fvo_free_cells(c); return -1; }
+    for (int cell = 0; cell < g->ncell; ++cell)
+      if (fvo_in_sweep(g, ranges, cell, n)) c->sweep[n][c->n_sweep[n]++] = cell;
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 #define FVO_DEFINE(T, SFX, SQRT, FABS)                                                          \
                                                                                                 \
@@ -153,27 +198,9 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
     return (*a < *b) ? *b : *a;                                                                 \
   }                                                                                             \
                                                                                                 \
-  /* does haloed cell `cell` take part in the flux/eigen sweep of axis n? */                    \
-  static inline int in_sweep_##SFX(const fvo_geom* g, int ranges, int cell, int n) {           \
-    for (int m = 0; m < g->dim; ++m) {                                                          \
-      const int cm = (cell / g->stride[m]) % g->S;                                              \
-      const int interior = (cm >= g->h && cm < g->P + g->h);                                    \
-      const int full_axis = (ranges == FVO_RANGES_HEAD) ? (m == n) : (m != n);                  \
-      if (!full_axis && !interior) return 0;                                                    \
-    }                                                                                           \
-    return 1;                                                                                   \
-  }                                                                                             \
-  static inline int is_interior_##SFX(const fvo_geom* g, int cell) {                           \
-    for (int m = 0; m < g->dim; ++m) {                                                          \
-      const int cm = (cell / g->stride[m]) % g->S;                                              \
-      if (cm < g->h || cm >= g->P + g->h) return 0;                                             \
-    }                                                                                           \
-    return 1;                                                                                   \
-  }                                                                                             \
-                                                                                                \
   /* One patch.  Scratch: Qc[ncell*nv], F[dim][ncell*nr], L[dim][ncell]. */                     \
-  static T patch_step_##SFX(const fvo_config* cfg, const fvo_geom* g, T* Q, T dt, T* Qc, T* F, \
-                            T* L) {                                                             \
+  static T patch_step_##SFX(const fvo_config* cfg, const fvo_geom* g, const fvo_cells* cl, T* Q, \
+                            T dt, T* Qc, T* F, T* L) {                                          \
     const int nv = g->nv, nr = g->nr, nc = g->ncell, dim = g->dim;                              \
     /* test.cpp:11-19 : copy every haloed cell, every variable */                               \
     memcpy(Qc, Q, sizeof(T) * (size_t)nc * nv);                                                 \
@@ -182,36 +209,38 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
     memset(L, 0, sizeof(T) * (size_t)dim * nc);                                                 \
     /* test.cpp:20-39 */                                                                        \
     for (int n = 0; n < dim; ++n)                                                               \
-      for (int c = 0; c < nc; ++c)                                                              \
-        if (in_sweep_##SFX(g, cfg->ranges, c, n)) {                                             \
-          T* f = F + ((size_t)n * nc + c) * nr;                                                 \
-          if (cfg->model == FVO_MODEL_EULER) euler_flux_##SFX(dim, Qc + (size_t)c * nv, n, f); \
-          else swe_flux_##SFX(Qc + (size_t)c * nv, n, f);                                       \
-        }                                                                                       \
+      for (int k = 0; k < cl->n_sweep[n]; ++k) {                                                \
+        const int c = cl->sweep[n][k];                                                          \
+        T* f = F + ((size_t)n * nc + c) * nr;                                                   \
+        if (cfg->model == FVO_MODEL_EULER) euler_flux_##SFX(dim, Qc + (size_t)c * nv, n, f);   \
+        else swe_flux_##SFX(Qc + (size_t)c * nv, n, f);                                         \
+      }                                                                                         \
     /* test.cpp:40-59 */                                                                        \
     for (int n = 0; n < dim; ++n)                                                               \
-      for (int c = 0; c < nc; ++c)                                                              \
-        if (in_sweep_##SFX(g, cfg->ranges, c, n))                                               \
-          L[(size_t)n * nc + c] = (cfg->model == FVO_MODEL_EULER)                               \
-                                      ? euler_eig_##SFX(dim, Qc + (size_t)c * nv, n)            \
-                                      : swe_eig_##SFX(Qc + (size_t)c * nv, n);                  \
+      for (int k = 0; k < cl->n_sweep[n]; ++k) {                                                \
+        const int c = cl->sweep[n][k];                                                          \
+        L[(size_t)n * nc + c] = (cfg->model == FVO_MODEL_EULER)                                 \
+                                    ? euler_eig_##SFX(dim, Qc + (size_t)c * nv, n)              \
+                                    : swe_eig_##SFX(Qc + (size_t)c * nv, n);                    \
+      }                                                                                         \
     /* test.cpp:60-77 : central flux difference, axis by axis in order */                       \
     for (int n = 0; n < dim; ++n) {                                                             \
       const int e = g->stride[n];                                                               \
       const T* f = F + (size_t)n * nc * nr;                                                     \
-      for (int c = 0; c < nc; ++c)                                                              \
-        if (is_interior_##SFX(g, c))                                                            \
-          for (int v = 0; v < nr; ++v)                                                          \
-            Qc[(size_t)c * nv + v] = Qc[(size_t)c * nv + v] - (T)0.5 * f[(size_t)(c + e) * nr + v] + \
-                                     (T)0.5 * f[(size_t)(c - e) * nr + v];                      \
+      for (int k = 0; k < cl->n_interior; ++k) {                                                \
+        const int c = cl->interior[k];                                                          \
+        for (int v = 0; v < nr; ++v)                                                            \
+          Qc[(size_t)c * nv + v] = Qc[(size_t)c * nv + v] - (T)0.5 * f[(size_t)(c + e) * nr + v] + \
+                                   (T)0.5 * f[(size_t)(c - e) * nr + v];                        \
+      }                                                                                         \
     }                                                                                           \
     /* test.cpp:78-95 : Rusanov dissipation from the ORIGINAL Q */                              \
     const int dv = (cfg->diss == FVO_DISS_ALL) ? nr : 1;                                        \
     for (int n = 0; n < dim; ++n) {                                                             \
       const int e = g->stride[n];                                                               \
       const T* l = L + (size_t)n * nc;                                                          \
-      for (int c = 0; c < nc; ++c)                                                              \
-        if (is_interior_##SFX(g, c))                                                            \
+      for (int k = 0; k < cl->n_interior; ++k) {                                                \
+        const int c = cl->interior[k];                                                          \
           for (int v = 0; v < dv; ++v)                                                          \
             Qc[(size_t)c * nv + v] =                                                            \
                 (T)0.5 * dt *                                                                   \
@@ -220,18 +249,21 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
                      (Q[(size_t)(c - e) * nv + v] - Q[(size_t)c * nv + v]) *                    \
                          maxp_##SFX(&l[c - e], &l[c])) +                                        \
                 Qc[(size_t)c * nv + v];                                                         \
+      }                                                                                         \
     }                                                                                           \
     /* test.cpp:96-104 : interior copy-back, all variables; plus the patch's max eigenvalue     \
      * over interior cells of the INPUT state (not in the reference) */         \
     T lam = (T)0;                                                                               \
-    for (int c = 0; c < nc; ++c)                                                                \
-      if (is_interior_##SFX(g, c)) {                                                            \
+    for (int k = 0; k < cl->n_interior; ++k) {                                                  \
+      {                                                                                         \
+        const int c = cl->interior[k];                                                          \
         for (int v = 0; v < nv; ++v) Q[(size_t)c * nv + v] = Qc[(size_t)c * nv + v];            \
         for (int n = 0; n < dim; ++n) { /* interior cells are swept under both range rules */  \
           const T ln = L[(size_t)n * nc + c];                                                   \
           if (lam < ln) lam = ln;                                                               \
         }                                                                                       \
       }                                                                                         \
+    }                                                                                           \
     return lam;                                                                                 \
   }                                                                                             \
                                                                                                 \
@@ -241,6 +273,8 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
     const int rc = fvo_make_geom(cfg, &g);                                                      \
     if (rc) return rc;                                                                          \
     if (n_patches < 0 || (!Q && n_patches > 0)) return -8;                                      \
+    fvo_cells cl;                                                                               \
+    if (fvo_make_cells(&g, cfg->ranges, &cl)) return -9;                                        \
     const size_t per = (size_t)g.ncell * g.nv;                                                  \
     const size_t scratch = per + (size_t)g.dim * g.ncell * (g.nr + 1);                          \
     T gmax = (T)0;                                                                              \
@@ -256,7 +290,7 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
         T* Qc = buf; T* F = Qc + per; T* L = F + (size_t)g.dim * g.ncell * g.nr;                \
         _Pragma("omp for schedule(static)")                                                     \
         for (int64_t b = 0; b < n_patches; ++b) {                                               \
-          const T lam = patch_step_##SFX(cfg, &g, Q + (size_t)b * per, dt, Qc, F, L);           \
+          const T lam = patch_step_##SFX(cfg, &g, &cl, Q + (size_t)b * per, dt, Qc, F, L);           \
           if (lambda_patch) lambda_patch[b] = lam;                                              \
           if (lmax < lam) lmax = lam;                                                           \
         }                                                                                       \
@@ -264,6 +298,7 @@ static void fvo_synth_cell(const fvo_config* c, int nv, int64_t cell, uint64_t s
       }                                                                                         \
       _Pragma("omp critical") { if (gmax < lmax) gmax = lmax; }                                 \
     }                                                                                           \
+    fvo_free_cells(&cl);                                                                        \
     if (fail) return -9;                                                                        \
     if (lambda_max) *lambda_max = gmax;                                                         \
     return 0;                                                                                   \
