@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="patches per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--output", default="unhaloed", choices=["unhaloed", "haloed"])
     ap.add_argument("--dissipation", default="var0", choices=["var0", "all"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cell"], help="3-D: plane-marching (auto) or thread-per-cell")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-sample", type=int, default=4096)
@@ -208,7 +209,8 @@ def main():
 
     model, dim, P, h, nr, na, dtype, batch, desc = WORKLOADS[args.workload]
     batch = args.batch or batch
-    upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=args.dissipation, output=args.output)
+    upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=args.dissipation, output=args.output,
+                              kernel=args.kernel)
     tdt = torch.float64 if dtype == "f64" else torch.float32
     npdt = np.float64 if dtype == "f64" else np.float32
     shard = PatchSharding(global_patches=batch * world, world_size=world, rank=rank)
@@ -309,7 +311,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": desc, "patches_per_gpu": batch, "global_patches": batch * world,
-                       "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)",
+                       "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)", "kernel_variant": args.kernel,
                        "parallelism": f"patch-sharded x{world}" + (", NCCL allreduce-max of lambda per step" if world > 1 else ""),
                        "l2": "inputs larger than L2: %.2f GB read + %.2f GB written per step per GPU"
                              % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
@@ -394,9 +396,10 @@ def time_variants(torch, runtime, args):
     for wl in ("c3", "c2", "c4", "c4f32", "c1"):
         model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
         tdt = torch.float64 if dtype == "f64" else torch.float32
-        for output in ("unhaloed", "haloed"):
-            for diss in ("var0", "all"):
-                upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output)
+        for output, diss, kern in [(o, d, k) for o in ("unhaloed", "haloed") for d in ("var0", "all")
+                                   for k in (("auto", "cell") if dim == 3 else ("auto",))]:
+            if True:
+                upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output, kernel=kern)
                 q_in = synthetic_on_device(torch, upd, 0, batch, tdt)
                 q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
                 lam = torch.zeros(1, dtype=tdt, device="cuda")
@@ -411,7 +414,7 @@ def time_variants(torch, runtime, args):
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / 10
                 gbs = upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9
-                res[f"{wl}/{output}/{diss}"] = {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
+                res[f"{wl}/{output}/{diss}" + ("/cell-kernel" if kern == "cell" else "")] = {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
                                                 "algorithmic_GBs": gbs}
                 del q_in, q_out
     return res

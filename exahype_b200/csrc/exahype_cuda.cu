@@ -58,7 +58,8 @@ int validate(const exahype_fv_config* cfg) {
   if (cfg->n_real < 1 || cfg->n_aux < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_real must be >= 1 and n_aux >= 0");
   if (cfg->dtype != EXAHYPE_DTYPE_F64 && cfg->dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
   if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
-  if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE))
+  if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE |
+                     EXAHYPE_FLAG_KERNEL_CELL))
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown flag bits 0x%x", cfg->flags);
   return EXAHYPE_OK;
 }
@@ -131,7 +132,9 @@ int exahype_cuda_fv_launch_info(const exahype_fv_config* cfg, int64_t n_patches,
   int rc = lookup(cfg, &e);
   if (rc) return rc;
   exahype::FvLaunchInfo info;
-  cudaError_t err = e->prepare[variant_of(cfg->flags)](&info, n_patches);
+  const int var = variant_of(cfg->flags);
+  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_prepare[var];
+  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches);
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_launch_info");
   if (grid) *grid = info.grid;
   if (block) *block = info.block;
@@ -157,7 +160,9 @@ int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must be 16-byte aligned (TMA bulk copies)");
   if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
-  cudaError_t err = e->launch[variant_of(cfg->flags)](q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);
+  const int var = variant_of(cfg->flags);
+  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  cudaError_t err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch");
   g_launches.fetch_add(1);
   return EXAHYPE_OK;

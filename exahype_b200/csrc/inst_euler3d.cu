@@ -1,6 +1,7 @@
 // Committed instantiations: compressible Euler, 3-D (5 unknowns), fp64 and fp32.
-// BASELINE.json config C3/C5: 8x8x8 patches + 1 halo -- one patch per tile, 512 threads = one per interior cell,
-// 40 000-byte tiles brought in by TMA bulk copies.
+// BASELINE.json config C3/C5: 8x8x8 patches + 1 halo.  Default kernel: plane marching (fv3d_march_kernel.cuh), 4 groups of
+// 3 warps per CTA, 4000-byte planes streamed through a 5-deep TMA ring.  Alternative (EXAHYPE_FLAG_KERNEL_CELL): the
+// thread-per-cell kernel, one patch per tile, 512 threads, 40 000-byte tiles by TMA.
 #include "fv_registry.h"
 
 namespace exahype {
@@ -8,11 +9,12 @@ namespace {
 using E3 = EulerPhysics<3, 5, 0>;
 
 const FvEntry kEntries[] = {
-    //                model                dtype              phys T      D  P  H  G   NT  MINB
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 3, 8, 1, 1, 512, 1),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 3, 8, 1, 1, 512, 1),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 3, 4, 1, 4, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 3, 4, 1, 4, 256, 2),
+    // plane-marching kernel (default): NG groups per CTA, ring of R planes | thread-per-cell kernel: G, NT, MINB
+    //                  model                dtype              phys T      P  H  NG R MINB | G   NT  MINB
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 8, 1, 4, 5, 1, 1, 512, 1),
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 8, 1, 4, 5, 1, 1, 512, 1),
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 4, 1, 6, 6, 1, 4, 256, 2),
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 4, 1, 6, 6, 1, 4, 256, 2),
 };
 }  // namespace
 

@@ -25,6 +25,7 @@ DTYPE = {"f64": 0, "f32": 1}
 FLAG_DISSIPATION_ALL = 1 << 0
 FLAG_OUTPUT_UNHALOED = 1 << 1
 FLAG_LAMBDA_ACCUMULATE = 1 << 2
+FLAG_KERNEL_CELL = 1 << 3
 
 ERR_NAMES = {-1: "INVALID_ARGUMENT", -2: "NO_INSTANTIATION", -3: "CUDA", -4: "NCCL", -5: "UNAVAILABLE"}
 
@@ -128,6 +129,7 @@ class PatchUpdate:
     dtype: str = "f64"
     dissipation: str = "var0"
     output: str = "haloed"
+    kernel: str = "auto"     # 'auto' | 'cell': 3-D shapes have a plane-marching kernel (auto) and a thread-per-cell one
 
     def __post_init__(self):
         from .KernelBuilder import viable
@@ -135,8 +137,9 @@ class PatchUpdate:
             raise Exception('check viability of inputs')          # reference KernelBuilder.py:52-53
         if self.model not in MODEL or self.dtype not in DTYPE:
             raise ValueError(f"unknown model/dtype {self.model}/{self.dtype}")
-        if self.dissipation not in ("var0", "all") or self.output not in ("haloed", "unhaloed"):
-            raise ValueError("dissipation must be 'var0'|'all', output 'haloed'|'unhaloed'")
+        if self.dissipation not in ("var0", "all") or self.output not in ("haloed", "unhaloed") \
+                or self.kernel not in ("auto", "cell"):
+            raise ValueError("dissipation must be 'var0'|'all', output 'haloed'|'unhaloed', kernel 'auto'|'cell'")
         self._lib = load()
 
     @classmethod
@@ -177,7 +180,8 @@ class PatchUpdate:
     def flags(self, accumulate_lambda: bool = False) -> int:
         return ((FLAG_DISSIPATION_ALL if self.dissipation == "all" else 0) |
                 (FLAG_OUTPUT_UNHALOED if self.output == "unhaloed" else 0) |
-                (FLAG_LAMBDA_ACCUMULATE if accumulate_lambda else 0))
+                (FLAG_LAMBDA_ACCUMULATE if accumulate_lambda else 0) |
+                (FLAG_KERNEL_CELL if self.kernel == "cell" else 0))
 
     def config(self, accumulate_lambda: bool = False) -> FvConfig:
         return FvConfig(MODEL[self.model], DTYPE[self.dtype], self.dim, self.patch_size, self.halo_size,

@@ -53,7 +53,10 @@ enum {
    * layout of q_in and only interior cells are written (q_out == q_in gives the reference's in-place update). */
   EXAHYPE_FLAG_OUTPUT_UNHALOED = 1u << 1,
   /* do not reset *lambda_max to 0 before the launch: fold this launch into the running maximum */
-  EXAHYPE_FLAG_LAMBDA_ACCUMULATE = 1u << 2
+  EXAHYPE_FLAG_LAMBDA_ACCUMULATE = 1u << 2,
+  /* 3-D shapes have two kernels with identical results: plane marching (default) and thread-per-cell (this flag).
+   * Ignored where only one kernel exists. */
+  EXAHYPE_FLAG_KERNEL_CELL = 1u << 3
 };
 
 typedef struct {
