@@ -101,254 +101,320 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Per-thread view of one warp group's stream of planes.  `seq` numbers the planes the group consumes, across patch
+// boundaries: plane seq lives in ring slot seq % R, scratch / window buffer seq % 3, staging buffer seq % 2.
+template <class C>
+struct MarchStream {
+  using T = typename C::T;
+  using Bits = typename FloatBits<T>::type;
+  const T* q_in;
+  T* q_out;
+  T* lambda_patch;
+  T *ring, *Fj, *Fk, *Lj, *Lk, *stage;
+  Bits* lam_slot;
+  unsigned long long* full;
+  long long g_index, n_groups;
+  T dt;
+  int n_seq;        // planes this group streams = patches * (P+2)
+  int gt, bar_id;
+  // consumer cursor
+  int seq, ip, pi, slot;
+  uint32_t parity;
+  // producer cursor (thread 0 of the group): next plane to request
+  int p_seq, p_ip, p_pi, p_slot;
+
+  __device__ __forceinline__ void issue_next_load() {
+    const long long patch = g_index + (long long)p_pi * n_groups;
+    mbar_expect_tx(&full[p_slot], C::PLANE_BYTES);
+    tma_load_1d(ring + p_slot * C::PLANE_ELEMS,
+                q_in + patch * (long long)C::PATCH_ELEMS + (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS,
+                C::PLANE_BYTES, &full[p_slot]);
+    ++p_seq;
+    if (++p_ip == C::NPL) { p_ip = 0; ++p_pi; }
+    if (++p_slot == C::R) p_slot = 0;
+  }
+  __device__ __forceinline__ const T* wait_plane() {
+    mbar_wait(&full[slot], parity);
+    return ring + slot * C::PLANE_ELEMS;
+  }
+  __device__ __forceinline__ const T* previous_plane() const {
+    return ring + (slot == 0 ? C::R - 1 : slot - 1) * C::PLANE_ELEMS;
+  }
+  __device__ __forceinline__ void advance() {
+    ++seq;
+    if (++ip == C::NPL) { ip = 0; ++pi; }
+    if (++slot == C::R) { slot = 0; parity ^= 1u; }
+  }
+
+  // After the group barrier of iteration `seq`: write out the plane staged in iteration seq-1 (if any).
+  // Executed by the interior warps; thread 0 issues the TMA stores.
+  __device__ __forceinline__ void drain_staged_plane(int n_drain_threads) {
+    if (seq == 0 || !(ip == 0 || ip >= 3)) return;          // the previous iteration updated a plane iff its ip >= 2
+    const int prev_pi = (ip == 0) ? pi - 1 : pi;
+    const int prev_plane = (ip == 0) ? C::P - 1 : ip - 3;    // zero-based interior plane
+    const long long patch = g_index + (long long)prev_pi * n_groups;
+    const T* sbuf = stage + ((seq - 1) & 1) * (C::STAGE_SEGS * C::SEG_PITCH);
+    if (C::UNHALOED) {
+      T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)prev_plane * C::OUT_PLANE_ELEMS;
+      if (C::USE_TMA_STORE) {
+        if (gt == 0) {
+#pragma unroll
+          for (int sgm = 0; sgm < C::STAGE_SEGS; ++sgm)
+            tma_store_1d(dst + sgm * C::SEG_ELEMS, sbuf + sgm * C::SEG_PITCH, C::SEG_ELEMS * (uint32_t)sizeof(T));
+          tma_store_commit();
+        }
+      } else {
+        for (int e = gt; e < C::OUT_PLANE_ELEMS; e += n_drain_threads) {
+          const int sgm = e / C::SEG_ELEMS;
+          dst[e] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+        }
+      }
+    } else {
+      // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
+      T* dst = q_out + patch * (long long)C::PATCH_ELEMS + (long long)(prev_plane + C::H) * C::PLANE_ELEMS;
+      constexpr int ROW = C::P * C::NV;
+      for (int e = gt; e < C::OUT_PLANE_ELEMS; e += n_drain_threads) {
+        const int row = e / ROW;
+        const int sgm = e / C::SEG_ELEMS;
+        dst[((row + C::H) * C::S + C::H) * C::NV + (e - row * ROW)] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+      }
+    }
+  }
+};
+
+// One plane for an interior column.  PH = seq % 3 is a compile-time phase, so the rolling window {old, mid, new}
+// is a renaming of three register sets and the scratch buffers have constant offsets.
+template <class C, int PH>
+__device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell, int sj, int sk, int st,
+                                                    typename C::T (&q)[3][C::NV], typename C::T (&fi)[3][C::NR],
+                                                    typename C::T (&li)[3], typename C::T (&lj)[3],
+                                                    typename C::T (&lk)[3], typename C::T& lam_local,
+                                                    typename FloatBits<typename C::T>::type& group_lam) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  using Upd = typename C::Upd;
+  using Bits = typename FloatBits<T>::type;
+  constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, S = C::S;
+  constexpr int NEW = PH, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
+  const int ip = ms.ip;
+
+  // ------------------------------------------------------------ evaluate plane ip
+  const T* __restrict__ qs = ms.wait_plane();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) q[NEW][v] = qs[cell * NV + v];
+  const auto pr = Phys::template prims<T>(q[NEW]);
+  Phys::template flux<0, T>(q[NEW], pr, fi[NEW]);
+  li[NEW] = Phys::template eigen<0, T>(q[NEW], pr);
+  if (ip >= 1 && ip <= C::P) {
+    T F[NR];
+    Phys::template flux<1, T>(q[NEW], pr, F);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) ms.Fj[(NEW * NR + v) * SJ + sj] = F[v];
+    lj[NEW] = Phys::template eigen<1, T>(q[NEW], pr);
+    ms.Lj[NEW * SJ + sj] = lj[NEW];
+    Phys::template flux<2, T>(q[NEW], pr, F);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) ms.Fk[(NEW * NR + v) * SK + sk] = F[v];
+    lk[NEW] = Phys::template eigen<2, T>(q[NEW], pr);
+    ms.Lk[NEW * SK + sk] = lk[NEW];
+    lam_local = fv_max(lam_local, fv_max(li[NEW], fv_max(lj[NEW], lk[NEW])));
+  }
+  // per-patch maximum eigenvalue over interior cells of the input state: published at the patch's last plane
+  if (ip == C::NPL - 1) {
+    T m = lam_local;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((ms.gt & 31) == 0) atomicMax(&ms.lam_slot[ms.pi & 1], FloatBits<T>::to(m));
+    lam_local = T(0);
+  }
+  if (C::USE_TMA_STORE && ms.gt == 0) tma_store_wait_read();   // staging buffer (seq & 1) is free again
+  named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+
+  // ------------------------------------------------------------ drain + prefetch
+  ms.drain_staged_plane(C::FACE_BASE);
+  if (ms.gt == 0) {
+    if (ms.seq >= 2 && ms.p_seq < ms.n_seq) ms.issue_next_load();   // the slot of plane seq-2 was last read in iteration seq-1
+    if (ip == 0 && ms.pi >= 1) {                                     // previous patch complete: publish its lambda
+      const Bits b = ms.lam_slot[(ms.pi - 1) & 1];
+      ms.lam_slot[(ms.pi - 1) & 1] = 0;
+      if (ms.lambda_patch) ms.lambda_patch[ms.g_index + (long long)(ms.pi - 1) * ms.n_groups] = FloatBits<T>::from(b);
+      group_lam = (b > group_lam) ? b : group_lam;
+    }
+  }
+
+  // ------------------------------------------------------------ update plane ip-1 (needs F_0 of planes ip-2 and ip)
+  if (ip >= 2) {
+    const T* __restrict__ qm = ms.previous_plane();      // plane ip-1: the neighbours' Q for the dissipation
+    const T dt = ms.dt;
+    T qc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) qc[v] = q[MID][v];
+    // "Q_copy = Q_copy - 0.5*F[+1] + 0.5*F[-1]" for axis 0, 1, 2 in order (test.cpp:60-77)
+#pragma unroll
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], fi[NEW][v], fi[OLD][v]);
+#pragma unroll
+    for (int v = 0; v < NR; ++v)
+      qc[v] = Upd::flux(qc[v], ms.Fj[(MID * NR + v) * SJ + sj + PJ], ms.Fj[(MID * NR + v) * SJ + sj - PJ]);
+#pragma unroll
+    for (int v = 0; v < NR; ++v)
+      qc[v] = Upd::flux(qc[v], ms.Fk[(MID * NR + v) * SK + sk + 1], ms.Fk[(MID * NR + v) * SK + sk - 1]);
+    // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
+#pragma unroll
+    for (int v = 0; v < C::DV; ++v)
+      qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q[OLD][v], li[MID], li[NEW], li[OLD], dt);
+    {
+      const T l_plus = ms.Lj[MID * SJ + sj + PJ], l_minus = ms.Lj[MID * SJ + sj - PJ];
+#pragma unroll
+      for (int v = 0; v < C::DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + S) * NV + v], qm[(cell - S) * NV + v], lj[MID], l_plus,
+                                 l_minus, dt);
+    }
+    {
+      const T l_plus = ms.Lk[MID * SK + sk + 1], l_minus = ms.Lk[MID * SK + sk - 1];
+#pragma unroll
+      for (int v = 0; v < C::DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[MID], l_plus,
+                                 l_minus, dt);
+    }
+    T* dst = ms.stage + (ms.seq & 1) * (C::STAGE_SEGS * C::SEG_PITCH) + st;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dst[v] = qc[v];
+    if (C::USE_TMA_STORE) fence_proxy_async_smem();
+  }
+  ms.advance();
+}
+
+// One plane for a face-halo column of axis AXIS (1 or 2): F_AXIS and L_AXIS of the cell one layer outside the interior.
+template <class C, int AXIS>
+__device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const typename C::T* __restrict__ qs, int cell,
+                                                int slot_in_scratch, int buf) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  T q[C::NV];
+#pragma unroll
+  for (int v = 0; v < C::NV; ++v) q[v] = qs[cell * C::NV + v];
+  const auto pr = Phys::template prims<T>(q);
+  T F[C::NR];
+  Phys::template flux<AXIS, T>(q, pr, F);
+  T* Fs = (AXIS == 1) ? ms.Fj : ms.Fk;
+  T* Ls = (AXIS == 1) ? ms.Lj : ms.Lk;
+  constexpr int SX = (AXIS == 1) ? C::SJ : C::SK;
+#pragma unroll
+  for (int v = 0; v < C::NR; ++v) Fs[(buf * C::NR + v) * SX + slot_in_scratch] = F[v];
+  Ls[buf * SX + slot_in_scratch] = Phys::template eigen<AXIS, T>(q, pr);
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
                   typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max) {
   using T = typename C::T;
-  using Phys = typename C::Phys;
-  using Upd = typename C::Upd;
   using Bits = typename FloatBits<T>::type;
   constexpr int P = C::P, H = C::H, S = C::S, NV = C::NV, NR = C::NR, R = C::R, NPL = C::NPL;
-  constexpr int SJ = C::SJ, SK = C::SK, PJ = C::PJ, PK = C::PK;
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int group = threadIdx.x / C::GROUP_THREADS;
   const int gt = threadIdx.x - group * C::GROUP_THREADS;      // thread within the group
   unsigned char* const gs = smem + group * C::GROUP_BYTES;
-  T* const ring = reinterpret_cast<T*>(gs + C::OFF_RING);
-  T* const Fj = reinterpret_cast<T*>(gs + C::OFF_FJ);          // [3][NR][SJ]
-  T* const Fk = reinterpret_cast<T*>(gs + C::OFF_FK);          // [3][NR][SK]
-  T* const Lj = reinterpret_cast<T*>(gs + C::OFF_LJ);          // [3][SJ]
-  T* const Lk = reinterpret_cast<T*>(gs + C::OFF_LK);          // [3][SK]
-  T* const stage = reinterpret_cast<T*>(gs + C::OFF_STAGE);    // [2][STAGE_SEGS * SEG_PITCH]
-  Bits* const lam_slot = reinterpret_cast<Bits*>(gs + C::OFF_LAM);   // [2] by patch parity
-  unsigned long long* const full = reinterpret_cast<unsigned long long*>(gs + C::OFF_BAR);   // [R]
+
+  MarchStream<C> ms;
+  ms.q_in = q_in; ms.q_out = q_out; ms.lambda_patch = lambda_patch; ms.dt = dt;
+  ms.ring = reinterpret_cast<T*>(gs + C::OFF_RING);
+  ms.Fj = reinterpret_cast<T*>(gs + C::OFF_FJ);          // [3][NR][SJ]
+  ms.Fk = reinterpret_cast<T*>(gs + C::OFF_FK);          // [3][NR][SK]
+  ms.Lj = reinterpret_cast<T*>(gs + C::OFF_LJ);          // [3][SJ]
+  ms.Lk = reinterpret_cast<T*>(gs + C::OFF_LK);          // [3][SK]
+  ms.stage = reinterpret_cast<T*>(gs + C::OFF_STAGE);    // [2][STAGE_SEGS * SEG_PITCH]
+  ms.lam_slot = reinterpret_cast<Bits*>(gs + C::OFF_LAM);   // [2] by patch parity
+  ms.full = reinterpret_cast<unsigned long long*>(gs + C::OFF_BAR);   // [R]
+  ms.gt = gt;
+  ms.bar_id = 1 + group;
 
   if (gt == 0) {
-    for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
-    lam_slot[0] = 0;
-    lam_slot[1] = 0;
+    for (int s = 0; s < R; ++s) mbar_init(&ms.full[s], 1);
+    ms.lam_slot[0] = 0;
+    ms.lam_slot[1] = 0;
     fence_mbar_init();
   }
   __syncthreads();   // the only CTA-wide barrier; groups are independent from here on
 
-  const long long n_groups = (long long)gridDim.x * C::NG;
-  const long long g_index = (long long)blockIdx.x * C::NG + group;
-  const long long my_patches = (n_patches > g_index) ? (n_patches - g_index + n_groups - 1) / n_groups : 0;
-  const long long n_seq = my_patches * NPL;                   // planes this group streams
-  const int bar_id = 1 + group;
-
-  // plane `seq` of this group's stream -> global source
-  auto issue_load = [&](long long seq) {
-    const long long pi = seq / NPL;
-    const int ip = (int)(seq - pi * NPL);
-    const long long patch = g_index + pi * n_groups;
-    const int slot = (int)(seq % R);
-    mbar_expect_tx(&full[slot], C::PLANE_BYTES);
-    tma_load_1d(ring + slot * C::PLANE_ELEMS,
-                q_in + patch * (long long)C::PATCH_ELEMS + (long long)(ip + H - 1) * C::PLANE_ELEMS,
-                C::PLANE_BYTES, &full[slot]);
-  };
+  ms.n_groups = (long long)gridDim.x * C::NG;
+  ms.g_index = (long long)blockIdx.x * C::NG + group;
+  const long long my_patches = (n_patches > ms.g_index) ? (n_patches - ms.g_index + ms.n_groups - 1) / ms.n_groups : 0;
+  ms.n_seq = (int)(my_patches * NPL);
+  ms.seq = ms.ip = ms.pi = ms.slot = 0;
+  ms.parity = 0;
+  ms.p_seq = ms.p_ip = ms.p_pi = ms.p_slot = 0;
   if (gt == 0)
-    for (long long s = 0; s < R && s < n_seq; ++s) issue_load(s);
+    for (int s = 0; s < R && ms.p_seq < ms.n_seq; ++s) ms.issue_next_load();
 
-  // ---- roles
-  const bool is_interior = gt < C::N_INT;
-  const bool is_face = gt >= C::FACE_BASE && gt < C::FACE_BASE + C::N_FACE;
-  int j = 0, k = 0;
-  if (is_interior) C::column(gt, j, k);
-  // face columns: f = 0..4P-1 -> [axis-1 low | axis-1 high | axis-2 low | axis-2 high], P columns each
-  const int f = gt - C::FACE_BASE;
-  const int f_axis = (f / (2 * P)) ? 2 : 1;
-  const int f_side = (f / P) & 1;
-  const int f_pos = f % P;
-  // cell within a haloed plane and scratch slot of this thread's column
-  const int cell = is_interior ? (j + H) * S + (k + H)
-                 : (f_axis == 1 ? (f_side ? H + P : H - 1) * S + (f_pos + H)
-                                : (f_pos + H) * S + (f_side ? H + P : H - 1));
-  const int sj = is_interior ? (j + 1) * PJ + k : (f_side ? P + 1 : 0) * PJ + f_pos;      // axis-1 scratch slot
-  const int sk = is_interior ? j * PK + (k + 1) : f_pos * PK + (f_side ? P + 1 : 0);      // axis-2 scratch slot
-  const int st = is_interior ? C::stage_index(j, k) : 0;
-
-  // ---- rolling window along axis 0 (interior columns)
-  T q_old[NV], q_mid[NV], q_new[NV];        // cell state of planes ip-2, ip-1, ip
-  T fi_old[NR], fi_mid[NR], fi_new[NR];     // F_0 of the same planes
-  T li_old = T(0), li_mid = T(0), li_new = T(0);
-  T lj_mid = T(0), lk_mid = T(0), lj_new = T(0), lk_new = T(0);
+  if (gt < C::FACE_BASE) {
+    // ======================================================== interior columns (whole warps; lanes past N_INT idle along)
+    int j = 0, k = 0;
+    const bool live = gt < C::N_INT;
+    if (live) C::column(gt, j, k);
+    const int cell = (j + H) * S + (k + H);
+    const int sj = (j + 1) * C::PJ + k;
+    const int sk = j * C::PK + (k + 1);
+    const int st = C::stage_index(j, k);
+    T q[3][NV], fi[3][NR], li[3], lj[3], lk[3];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) q_old[v] = q_mid[v] = q_new[v] = T(0);
+    for (int w = 0; w < 3; ++w) {
 #pragma unroll
-  for (int v = 0; v < NR; ++v) fi_old[v] = fi_mid[v] = fi_new[v] = T(0);
-  T lam_local = T(0);
-  Bits group_lam = 0;
-
-  long long pi = 0;     // patch counter of this group
-  int ip = 0;           // plane within the patch, 0 .. P+1
-  for (long long seq = 0; seq <= n_seq; ++seq) {
-    const int buf = (int)(seq % 3);
-    const bool have_plane = seq < n_seq;      // the extra iteration only drains the last staged plane
-    if (have_plane) {
-      const int slot = (int)(seq % R);
-      mbar_wait(&full[slot], (uint32_t)((seq / R) & 1));
-      const T* __restrict__ qs = ring + slot * C::PLANE_ELEMS;
-      const bool inner_plane = (ip >= 1 && ip <= P);
-
-      // ------------------------------------------------------------ evaluate plane ip
-      if (is_interior) {
+      for (int v = 0; v < NV; ++v) q[w][v] = T(0);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) q_new[v] = qs[cell * NV + v];
-        const auto pr = Phys::template prims<T>(q_new);
-        Phys::template flux<0, T>(q_new, pr, fi_new);
-        li_new = Phys::template eigen<0, T>(q_new, pr);
-        if (inner_plane) {
-          T F[NR];
-          Phys::template flux<1, T>(q_new, pr, F);
-#pragma unroll
-          for (int v = 0; v < NR; ++v) Fj[(buf * NR + v) * SJ + sj] = F[v];
-          lj_new = Phys::template eigen<1, T>(q_new, pr);
-          Lj[buf * SJ + sj] = lj_new;
-          Phys::template flux<2, T>(q_new, pr, F);
-#pragma unroll
-          for (int v = 0; v < NR; ++v) Fk[(buf * NR + v) * SK + sk] = F[v];
-          lk_new = Phys::template eigen<2, T>(q_new, pr);
-          Lk[buf * SK + sk] = lk_new;
-          lam_local = fv_max(lam_local, fv_max(li_new, fv_max(lj_new, lk_new)));
-        }
-      } else if (is_face && inner_plane) {
-        T q[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) q[v] = qs[cell * NV + v];
-        const auto pr = Phys::template prims<T>(q);
-        T F[NR];
-        if (f_axis == 1) {
-          Phys::template flux<1, T>(q, pr, F);
-#pragma unroll
-          for (int v = 0; v < NR; ++v) Fj[(buf * NR + v) * SJ + sj] = F[v];
-          Lj[buf * SJ + sj] = Phys::template eigen<1, T>(q, pr);
-        } else {
-          Phys::template flux<2, T>(q, pr, F);
-#pragma unroll
-          for (int v = 0; v < NR; ++v) Fk[(buf * NR + v) * SK + sk] = F[v];
-          Lk[buf * SK + sk] = Phys::template eigen<2, T>(q, pr);
-        }
-      }
-      // per-patch maximum eigenvalue over interior cells of the input state: published at the patch's last plane
-      if (ip == NPL - 1 && is_interior) {
-        T m = lam_local;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((gt & 31) == 0) atomicMax(&lam_slot[pi & 1], FloatBits<T>::to(m));
-        lam_local = T(0);
-      }
+      for (int v = 0; v < NR; ++v) fi[w][v] = T(0);
+      li[w] = lj[w] = lk[w] = T(0);
     }
-    if (C::USE_TMA_STORE && gt == 0) tma_store_wait_read();   // staging buffer (seq & 1) is free again
-    named_barrier_sync(bar_id, C::GROUP_THREADS);
-
-    // ------------------------------------------------------------ after the barrier: drain + prefetch (one thread)
-    // the plane staged in the previous iteration belongs to (patch, plane) = previous (pi, ip) - 1
-    const bool staged_prev = (seq >= 1) && ((ip == 0) ? true : (ip >= 3));   // previous iteration had ip_prev >= 2
-    long long prev_pi = pi;
-    int prev_plane = ip - 3;            // zero-based interior plane written in the previous iteration
-    if (ip == 0) { prev_pi = pi - 1; prev_plane = P - 1; }
-    if (staged_prev && prev_pi >= 0) {
-      const long long patch = g_index + prev_pi * n_groups;
-      const T* sbuf = stage + ((seq - 1) & 1) * (C::STAGE_SEGS * C::SEG_PITCH);
-      if (C::UNHALOED) {
-        T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)prev_plane * C::OUT_PLANE_ELEMS;
-        if (C::USE_TMA_STORE) {
-          if (gt == 0) {
-#pragma unroll
-            for (int sgm = 0; sgm < C::STAGE_SEGS; ++sgm)
-              tma_store_1d(dst + sgm * C::SEG_ELEMS, sbuf + sgm * C::SEG_PITCH, C::SEG_ELEMS * (uint32_t)sizeof(T));
-            tma_store_commit();
-          }
-        } else {
-          for (int e = gt; e < C::OUT_PLANE_ELEMS; e += C::GROUP_THREADS) {
-            const int sgm = e / C::SEG_ELEMS;
-            dst[e] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
-          }
-        }
-      } else {
-        // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
-        T* dst = q_out + patch * (long long)C::PATCH_ELEMS + (long long)(prev_plane + H) * C::PLANE_ELEMS;
-        constexpr int ROW = P * NV;
-        for (int e = gt; e < C::OUT_PLANE_ELEMS; e += C::GROUP_THREADS) {
-          const int row = e / ROW;
-          const int sgm = e / C::SEG_ELEMS;
-          dst[((row + H) * S + H) * NV + (e - row * ROW)] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
-        }
-      }
+    T lam_local = T(0);
+    Bits group_lam = 0;
+    // lanes past N_INT (patch sizes whose P*P is not a multiple of 32) recompute column (0,0) and write the same
+    // values to the same places as lane 0: harmless, and it keeps every warp whole for the shuffles and barriers
+    while (true) {
+      if (ms.seq >= ms.n_seq) break;
+      march_interior_step<C, 0>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
+      if (ms.seq >= ms.n_seq) break;
+      march_interior_step<C, 1>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
+      if (ms.seq >= ms.n_seq) break;
+      march_interior_step<C, 2>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
     }
+    // one more barrier round drains the last staged plane
+    if (C::USE_TMA_STORE && gt == 0) tma_store_wait_read();
+    named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+    ms.drain_staged_plane(C::FACE_BASE);
     if (gt == 0) {
-      if (seq >= 2 && seq - 2 + R < n_seq) issue_load(seq - 2 + R);   // slot of plane seq-2 was last read in iteration seq-1
-      if (have_plane && ip == 0 && pi >= 1) {                          // previous patch is complete: publish its lambda
-        const Bits b = lam_slot[(pi - 1) & 1];
-        lam_slot[(pi - 1) & 1] = 0;
-        if (lambda_patch) lambda_patch[g_index + (pi - 1) * n_groups] = FloatBits<T>::from(b);
+      if (C::USE_TMA_STORE) tma_store_wait_all();
+      if (my_patches > 0) {
+        const Bits b = ms.lam_slot[(my_patches - 1) & 1];
+        if (lambda_patch) lambda_patch[ms.g_index + (my_patches - 1) * ms.n_groups] = FloatBits<T>::from(b);
         group_lam = (b > group_lam) ? b : group_lam;
       }
+      if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
     }
-    if (!have_plane) break;
-
-    // ------------------------------------------------------------ update plane ip-1 (needs F_0 of planes ip-2 and ip)
-    if (is_interior && ip >= 2) {
-      const int ub = (int)((seq + 2) % 3);      // scratch buffer of plane ip-1, written in the previous iteration
-      const T* __restrict__ qm = ring + (int)((seq - 1) % R) * C::PLANE_ELEMS;   // plane ip-1, for the neighbours' Q
-      T qc[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) qc[v] = q_mid[v];
-      // "Q_copy = Q_copy - 0.5*F[+1] + 0.5*F[-1]" for axis 0, 1, 2 in order (test.cpp:60-77)
-#pragma unroll
-      for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], fi_new[v], fi_old[v]);
-#pragma unroll
-      for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], Fj[(ub * NR + v) * SJ + sj + PJ], Fj[(ub * NR + v) * SJ + sj - PJ]);
-#pragma unroll
-      for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], Fk[(ub * NR + v) * SK + sk + 1], Fk[(ub * NR + v) * SK + sk - 1]);
-      // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
-#pragma unroll
-      for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], q_mid[v], q_new[v], q_old[v], li_mid, li_new, li_old, dt);
-      {
-        const T l_plus = Lj[ub * SJ + sj + PJ], l_minus = Lj[ub * SJ + sj - PJ];
-#pragma unroll
-        for (int v = 0; v < C::DV; ++v)
-          qc[v] = Upd::dissipation(qc[v], q_mid[v], qm[(cell + S) * NV + v], qm[(cell - S) * NV + v], lj_mid, l_plus,
-                                   l_minus, dt);
+  } else {
+    // ======================================================== face-halo columns of axes 1 and 2
+    // f = 0..4P-1 -> [axis-1 low | axis-1 high | axis-2 low | axis-2 high], P columns each
+    const int f = gt - C::FACE_BASE;
+    const bool live = f < C::N_FACE;
+    const int f_axis = (f / (2 * P)) ? 2 : 1;
+    const int f_side = (f / P) & 1;
+    const int f_pos = f % P;
+    const int edge = f_side ? H + P : H - 1;
+    const int cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
+    const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos
+                                              : f_pos * C::PK + (f_side ? P + 1 : 0);
+    int buf = 0;
+    while (ms.seq < ms.n_seq) {
+      const T* __restrict__ qs = ms.wait_plane();
+      if (live && ms.ip >= 1 && ms.ip <= P) {
+        if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, buf);
+        else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, buf);
       }
-      {
-        const T l_plus = Lk[ub * SK + sk + 1], l_minus = Lk[ub * SK + sk - 1];
-#pragma unroll
-        for (int v = 0; v < C::DV; ++v)
-          qc[v] = Upd::dissipation(qc[v], q_mid[v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk_mid, l_plus,
-                                   l_minus, dt);
-      }
-      T* dst = stage + (seq & 1) * (C::STAGE_SEGS * C::SEG_PITCH) + st;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) dst[v] = qc[v];
-      if (C::USE_TMA_STORE) fence_proxy_async_smem();
+      named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+      ms.advance();
+      if (++buf == 3) buf = 0;
     }
-    // ------------------------------------------------------------ rotate the window
-    if (is_interior) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) { q_old[v] = q_mid[v]; q_mid[v] = q_new[v]; }
-#pragma unroll
-      for (int v = 0; v < NR; ++v) { fi_old[v] = fi_mid[v]; fi_mid[v] = fi_new[v]; }
-      li_old = li_mid; li_mid = li_new;
-      lj_mid = lj_new; lk_mid = lk_new;
-    }
-    if (++ip == NPL) { ip = 0; ++pi; }
-  }
-
-  // the extra iteration above staged nothing new; publish the last patch's lambda and the group maximum
-  if (gt == 0) {
-    if (C::USE_TMA_STORE) tma_store_wait_all();
-    if (my_patches > 0) {
-      const Bits b = lam_slot[(my_patches - 1) & 1];
-      if (lambda_patch) lambda_patch[g_index + (my_patches - 1) * n_groups] = FloatBits<T>::from(b);
-      group_lam = (b > group_lam) ? b : group_lam;
-    }
-    if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
+    named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
   }
 }
 
