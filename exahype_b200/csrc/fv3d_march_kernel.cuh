@@ -8,7 +8,7 @@
 //
 //   * thread <-> column (j,k).  The axis-0 stencil lives in registers: a rolling window {i-1, i, i+1} of the cell
 //     state, F_0 and L_0.  Nothing of axis 0 ever touches shared memory.
-//   * only the current plane's F_1, F_2, L_1, L_2 go through shared scratch (three rotating plane buffers -> one
+//   * only the current plane's F_1, F_2, L_1, L_2 go through shared scratch (two alternating plane buffers, one
 //     named barrier per plane, 3 warps wide for 8x8x8 patches);  face-halo columns of axes 1 and 2 are evaluated by
 //     the group's last warp(s).
 //   * planes stream HBM -> shared memory through a ring of R plane buffers filled by 1-D TMA bulk copies
@@ -70,10 +70,10 @@ struct Fv3dMarchConfig {
   // per-group shared memory
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_FJ = align_up(OFF_RING + R * PLANE_BYTES, 16);
-  static constexpr int OFF_FK = align_up(OFF_FJ + 3 * NR * SJ * (int)sizeof(T), 16);
-  static constexpr int OFF_LJ = align_up(OFF_FK + 3 * NR * SK * (int)sizeof(T), 16);
-  static constexpr int OFF_LK = align_up(OFF_LJ + 3 * SJ * (int)sizeof(T), 16);
-  static constexpr int OFF_STAGE = align_up(OFF_LK + 3 * SK * (int)sizeof(T), 128);
+  static constexpr int OFF_FK = align_up(OFF_FJ + 2 * NR * SJ * (int)sizeof(T), 16);
+  static constexpr int OFF_LJ = align_up(OFF_FK + 2 * NR * SK * (int)sizeof(T), 16);
+  static constexpr int OFF_LK = align_up(OFF_LJ + 2 * SJ * (int)sizeof(T), 16);
+  static constexpr int OFF_STAGE = align_up(OFF_LK + 2 * SK * (int)sizeof(T), 128);
   static constexpr int OFF_LAM = align_up(OFF_STAGE + 2 * STAGE_SEGS * SEG_PITCH * (int)sizeof(T), 16);
   static constexpr int OFF_BAR = align_up(OFF_LAM + 2 * 8, 16);
   static constexpr int GROUP_BYTES = align_up(OFF_BAR + R * 8, 128);
@@ -146,16 +146,14 @@ struct MarchStream {
     if (++slot == C::R) { slot = 0; parity ^= 1u; }
   }
 
-  // After the group barrier of iteration `seq`: write out the plane staged in iteration seq-1 (if any).
-  // Executed by the interior warps; thread 0 issues the TMA stores.
+  // After the group barrier of iteration `seq`: write out the plane updated (staged) in this iteration, i.e. interior
+  // plane ip-2 of patch pi.  Executed by the interior warps; thread 0 issues the TMA stores.
   __device__ __forceinline__ void drain_staged_plane(int n_drain_threads) {
-    if (seq == 0 || !(ip == 0 || ip >= 3)) return;          // the previous iteration updated a plane iff its ip >= 2
-    const int prev_pi = (ip == 0) ? pi - 1 : pi;
-    const int prev_plane = (ip == 0) ? C::P - 1 : ip - 3;    // zero-based interior plane
-    const long long patch = g_index + (long long)prev_pi * n_groups;
-    const T* sbuf = stage + ((seq - 1) & 1) * (C::STAGE_SEGS * C::SEG_PITCH);
+    const int plane = ip - 2;                                // zero-based interior plane
+    const long long patch = g_index + (long long)pi * n_groups;
+    const T* sbuf = stage + (seq & 1) * (C::STAGE_SEGS * C::SEG_PITCH);
     if (C::UNHALOED) {
-      T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)prev_plane * C::OUT_PLANE_ELEMS;
+      T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)plane * C::OUT_PLANE_ELEMS;
       if (C::USE_TMA_STORE) {
         if (gt == 0) {
 #pragma unroll
@@ -171,7 +169,7 @@ struct MarchStream {
       }
     } else {
       // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
-      T* dst = q_out + patch * (long long)C::PATCH_ELEMS + (long long)(prev_plane + C::H) * C::PLANE_ELEMS;
+      T* dst = q_out + patch * (long long)C::PATCH_ELEMS + (long long)(plane + C::H) * C::PLANE_ELEMS;
       constexpr int ROW = C::P * C::NV;
       for (int e = gt; e < C::OUT_PLANE_ELEMS; e += n_drain_threads) {
         const int row = e / ROW;
@@ -183,7 +181,11 @@ struct MarchStream {
 };
 
 // One plane for an interior column.  PH = seq % 3 is a compile-time phase, so the rolling window {old, mid, new}
-// is a renaming of three register sets and the scratch buffers have constant offsets.
+// is a renaming of three register sets.  Order inside one iteration:
+//   load plane ip, F_0 / L_0 (registers)  ->  update plane ip-1 (reads scratch of plane ip-1, written last iteration)
+//   ->  F_1, F_2, L_1, L_2 of plane ip into the other scratch buffer  ->  group barrier  ->  drain the updated plane.
+// The scratch buffer written here was last read before the previous barrier, so two buffers and one barrier per plane
+// are enough.
 template <class C, int PH>
 __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell, int sj, int sk, int st,
                                                     typename C::T (&q)[3][C::NV], typename C::T (&fi)[3][C::NR],
@@ -197,50 +199,19 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, S = C::S;
   constexpr int NEW = PH, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
   const int ip = ms.ip;
+  const int wb = ms.seq & 1;                 // scratch / staging buffer of this iteration
+  T* __restrict__ const FjW = ms.Fj + wb * (NR * SJ);
+  T* __restrict__ const FkW = ms.Fk + wb * (NR * SK);
+  const T* __restrict__ const FjR = ms.Fj + (wb ^ 1) * (NR * SJ);
+  const T* __restrict__ const FkR = ms.Fk + (wb ^ 1) * (NR * SK);
 
-  // ------------------------------------------------------------ evaluate plane ip
+  // ------------------------------------------------------------ plane ip: state, F_0, L_0 into the window
   const T* __restrict__ qs = ms.wait_plane();
 #pragma unroll
   for (int v = 0; v < NV; ++v) q[NEW][v] = qs[cell * NV + v];
   const auto pr = Phys::template prims<T>(q[NEW]);
   Phys::template flux<0, T>(q[NEW], pr, fi[NEW]);
   li[NEW] = Phys::template eigen<0, T>(q[NEW], pr);
-  if (ip >= 1 && ip <= C::P) {
-    T F[NR];
-    Phys::template flux<1, T>(q[NEW], pr, F);
-#pragma unroll
-    for (int v = 0; v < NR; ++v) ms.Fj[(NEW * NR + v) * SJ + sj] = F[v];
-    lj[NEW] = Phys::template eigen<1, T>(q[NEW], pr);
-    ms.Lj[NEW * SJ + sj] = lj[NEW];
-    Phys::template flux<2, T>(q[NEW], pr, F);
-#pragma unroll
-    for (int v = 0; v < NR; ++v) ms.Fk[(NEW * NR + v) * SK + sk] = F[v];
-    lk[NEW] = Phys::template eigen<2, T>(q[NEW], pr);
-    ms.Lk[NEW * SK + sk] = lk[NEW];
-    lam_local = fv_max(lam_local, fv_max(li[NEW], fv_max(lj[NEW], lk[NEW])));
-  }
-  // per-patch maximum eigenvalue over interior cells of the input state: published at the patch's last plane
-  if (ip == C::NPL - 1) {
-    T m = lam_local;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((ms.gt & 31) == 0) atomicMax(&ms.lam_slot[ms.pi & 1], FloatBits<T>::to(m));
-    lam_local = T(0);
-  }
-  if (C::USE_TMA_STORE && ms.gt == 0) tma_store_wait_read();   // staging buffer (seq & 1) is free again
-  named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
-
-  // ------------------------------------------------------------ drain + prefetch
-  ms.drain_staged_plane(C::FACE_BASE);
-  if (ms.gt == 0) {
-    if (ms.seq >= 2 && ms.p_seq < ms.n_seq) ms.issue_next_load();   // the slot of plane seq-2 was last read in iteration seq-1
-    if (ip == 0 && ms.pi >= 1) {                                     // previous patch complete: publish its lambda
-      const Bits b = ms.lam_slot[(ms.pi - 1) & 1];
-      ms.lam_slot[(ms.pi - 1) & 1] = 0;
-      if (ms.lambda_patch) ms.lambda_patch[ms.g_index + (long long)(ms.pi - 1) * ms.n_groups] = FloatBits<T>::from(b);
-      group_lam = (b > group_lam) ? b : group_lam;
-    }
-  }
 
   // ------------------------------------------------------------ update plane ip-1 (needs F_0 of planes ip-2 and ip)
   if (ip >= 2) {
@@ -253,33 +224,73 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
 #pragma unroll
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], fi[NEW][v], fi[OLD][v]);
 #pragma unroll
-    for (int v = 0; v < NR; ++v)
-      qc[v] = Upd::flux(qc[v], ms.Fj[(MID * NR + v) * SJ + sj + PJ], ms.Fj[(MID * NR + v) * SJ + sj - PJ]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FjR[v * SJ + sj + PJ], FjR[v * SJ + sj - PJ]);
 #pragma unroll
-    for (int v = 0; v < NR; ++v)
-      qc[v] = Upd::flux(qc[v], ms.Fk[(MID * NR + v) * SK + sk + 1], ms.Fk[(MID * NR + v) * SK + sk - 1]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + sk + 1], FkR[v * SK + sk - 1]);
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
 #pragma unroll
     for (int v = 0; v < C::DV; ++v)
       qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q[OLD][v], li[MID], li[NEW], li[OLD], dt);
     {
-      const T l_plus = ms.Lj[MID * SJ + sj + PJ], l_minus = ms.Lj[MID * SJ + sj - PJ];
+      const T* __restrict__ LjR = ms.Lj + (wb ^ 1) * SJ;
+      const T l_plus = LjR[sj + PJ], l_minus = LjR[sj - PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + S) * NV + v], qm[(cell - S) * NV + v], lj[MID], l_plus,
                                  l_minus, dt);
     }
     {
-      const T l_plus = ms.Lk[MID * SK + sk + 1], l_minus = ms.Lk[MID * SK + sk - 1];
+      const T* __restrict__ LkR = ms.Lk + (wb ^ 1) * SK;
+      const T l_plus = LkR[sk + 1], l_minus = LkR[sk - 1];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[MID], l_plus,
                                  l_minus, dt);
     }
-    T* dst = ms.stage + (ms.seq & 1) * (C::STAGE_SEGS * C::SEG_PITCH) + st;
+    T* dst = ms.stage + wb * (C::STAGE_SEGS * C::SEG_PITCH) + st;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = qc[v];
     if (C::USE_TMA_STORE) fence_proxy_async_smem();
+  }
+
+  // ------------------------------------------------------------ plane ip: F_1, F_2, L_1, L_2 for the neighbours
+  if (ip >= 1 && ip <= C::P) {
+    T F[NR];
+    Phys::template flux<1, T>(q[NEW], pr, F);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) FjW[v * SJ + sj] = F[v];
+    lj[NEW] = Phys::template eigen<1, T>(q[NEW], pr);
+    ms.Lj[wb * SJ + sj] = lj[NEW];
+    Phys::template flux<2, T>(q[NEW], pr, F);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) FkW[v * SK + sk] = F[v];
+    lk[NEW] = Phys::template eigen<2, T>(q[NEW], pr);
+    ms.Lk[wb * SK + sk] = lk[NEW];
+    lam_local = fv_max(lam_local, fv_max(li[NEW], fv_max(lj[NEW], lk[NEW])));
+  }
+  // per-patch maximum eigenvalue over interior cells of the input state: complete at the patch's last plane
+  const bool last_plane = (ip == C::NPL - 1);
+  if (last_plane) {
+    T m = lam_local;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((ms.gt & 31) == 0) atomicMax(&ms.lam_slot[ms.pi & 1], FloatBits<T>::to(m));
+    lam_local = T(0);
+  }
+  if (C::USE_TMA_STORE && ms.gt == 0) tma_store_wait_read();   // the other staging buffer is free for the next iteration
+  named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+
+  // ------------------------------------------------------------ drain, prefetch, publish
+  if (ip >= 2) ms.drain_staged_plane(C::FACE_BASE);
+  if (ms.gt == 0) {
+    // plane seq-1 was last read by the update above: its ring slot takes plane seq-1+R
+    if (ms.seq >= 1 && ms.p_seq < ms.n_seq) ms.issue_next_load();
+    if (last_plane) {
+      const Bits b = ms.lam_slot[ms.pi & 1];
+      ms.lam_slot[ms.pi & 1] = 0;                           // next used two patches from now
+      if (ms.lambda_patch) ms.lambda_patch[ms.g_index + (long long)ms.pi * ms.n_groups] = FloatBits<T>::from(b);
+      group_lam = (b > group_lam) ? b : group_lam;
+    }
   }
   ms.advance();
 }
@@ -320,10 +331,10 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   MarchStream<C> ms;
   ms.q_in = q_in; ms.q_out = q_out; ms.lambda_patch = lambda_patch; ms.dt = dt;
   ms.ring = reinterpret_cast<T*>(gs + C::OFF_RING);
-  ms.Fj = reinterpret_cast<T*>(gs + C::OFF_FJ);          // [3][NR][SJ]
-  ms.Fk = reinterpret_cast<T*>(gs + C::OFF_FK);          // [3][NR][SK]
-  ms.Lj = reinterpret_cast<T*>(gs + C::OFF_LJ);          // [3][SJ]
-  ms.Lk = reinterpret_cast<T*>(gs + C::OFF_LK);          // [3][SK]
+  ms.Fj = reinterpret_cast<T*>(gs + C::OFF_FJ);          // [2][NR][SJ]
+  ms.Fk = reinterpret_cast<T*>(gs + C::OFF_FK);          // [2][NR][SK]
+  ms.Lj = reinterpret_cast<T*>(gs + C::OFF_LJ);          // [2][SJ]
+  ms.Lk = reinterpret_cast<T*>(gs + C::OFF_LK);          // [2][SK]
   ms.stage = reinterpret_cast<T*>(gs + C::OFF_STAGE);    // [2][STAGE_SEGS * SEG_PITCH]
   ms.lam_slot = reinterpret_cast<Bits*>(gs + C::OFF_LAM);   // [2] by patch parity
   ms.full = reinterpret_cast<unsigned long long*>(gs + C::OFF_BAR);   // [R]
@@ -378,17 +389,8 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
       if (ms.seq >= ms.n_seq) break;
       march_interior_step<C, 2>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
     }
-    // one more barrier round drains the last staged plane
-    if (C::USE_TMA_STORE && gt == 0) tma_store_wait_read();
-    named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
-    ms.drain_staged_plane(C::FACE_BASE);
     if (gt == 0) {
       if (C::USE_TMA_STORE) tma_store_wait_all();
-      if (my_patches > 0) {
-        const Bits b = ms.lam_slot[(my_patches - 1) & 1];
-        if (lambda_patch) lambda_patch[ms.g_index + (my_patches - 1) * ms.n_groups] = FloatBits<T>::from(b);
-        group_lam = (b > group_lam) ? b : group_lam;
-      }
       if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
     }
   } else {
@@ -403,18 +405,15 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     const int cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
     const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos
                                               : f_pos * C::PK + (f_side ? P + 1 : 0);
-    int buf = 0;
     while (ms.seq < ms.n_seq) {
       const T* __restrict__ qs = ms.wait_plane();
       if (live && ms.ip >= 1 && ms.ip <= P) {
-        if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, buf);
-        else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, buf);
+        if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, ms.seq & 1);
+        else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, ms.seq & 1);
       }
       named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
       ms.advance();
-      if (++buf == 3) buf = 0;
     }
-    named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
   }
 }
 

@@ -11,8 +11,8 @@ using E3 = EulerPhysics<3, 5, 0>;
 const FvEntry kEntries[] = {
     // plane-marching kernel (default): NG groups per CTA, ring of R planes | thread-per-cell kernel: G, NT, MINB
     //                  model                dtype              phys T      P  H  NG R MINB | G   NT  MINB
-    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 8, 1, 4, 5, 1, 1, 512, 1),
-    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 8, 1, 4, 5, 1, 1, 512, 1),
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 8, 1, 5, 5, 1, 1, 512, 1),
+    EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 8, 1, 5, 5, 1, 1, 512, 1),
     EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E3, double, 4, 1, 6, 6, 1, 4, 256, 2),
     EXAHYPE_FV3D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E3, float, 4, 1, 6, 6, 1, 4, 256, 2),
 };
