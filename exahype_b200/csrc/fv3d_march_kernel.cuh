@@ -101,8 +101,9 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Per-thread view of one warp group's stream of planes.  `seq` numbers the planes the group consumes, across patch
-// boundaries: plane seq lives in ring slot seq % R, scratch / window buffer seq % 3, staging buffer seq % 2.
+// Per-thread view of one warp group's stream of planes.  The group consumes planes 0..P+1 of its patches back to back;
+// plane n of the stream lives in ring slot n % R; within a patch, plane ip uses register-window set ip % 3 and
+// scratch / staging buffer ip % 2 (all compile-time: the per-patch plane loop is fully unrolled).
 template <class C>
 struct MarchStream {
   using T = typename C::T;
@@ -116,9 +117,10 @@ struct MarchStream {
   long long g_index, n_groups;
   T dt;
   int n_seq;        // planes this group streams = patches * (P+2)
+  int n_my_patches;
   int gt, bar_id;
-  // consumer cursor
-  int seq, ip, pi, slot;
+  // consumer cursor: patch counter and ring slot (+ mbarrier phase parity) of the next plane
+  int pi, slot;
   uint32_t parity;
   // producer cursor (thread 0 of the group): next plane to request
   int p_seq, p_ip, p_pi, p_slot;
@@ -140,18 +142,15 @@ struct MarchStream {
   __device__ __forceinline__ const T* previous_plane() const {
     return ring + (slot == 0 ? C::R - 1 : slot - 1) * C::PLANE_ELEMS;
   }
-  __device__ __forceinline__ void advance() {
-    ++seq;
-    if (++ip == C::NPL) { ip = 0; ++pi; }
+  __device__ __forceinline__ void advance_plane() {          // ring cursor only; the plane index is compile-time
     if (++slot == C::R) { slot = 0; parity ^= 1u; }
   }
 
-  // After the group barrier of iteration `seq`: write out the plane updated (staged) in this iteration, i.e. interior
-  // plane ip-2 of patch pi.  Executed by the interior warps; thread 0 issues the TMA stores.
-  __device__ __forceinline__ void drain_staged_plane(int n_drain_threads) {
-    const int plane = ip - 2;                                // zero-based interior plane
+  // After the group barrier of an iteration: write out the plane updated (staged) in it -- zero-based interior plane
+  // `plane` of patch pi, sitting in staging buffer `buffer`.  Executed by the interior warps; thread 0 issues the TMA stores.
+  __device__ __forceinline__ void drain_staged_plane(int plane, int buffer, int n_drain_threads) {
     const long long patch = g_index + (long long)pi * n_groups;
-    const T* sbuf = stage + (seq & 1) * (C::STAGE_SEGS * C::SEG_PITCH);
+    const T* sbuf = stage + buffer * (C::STAGE_SEGS * C::SEG_PITCH);
     if (C::UNHALOED) {
       T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)plane * C::OUT_PLANE_ELEMS;
       if (C::USE_TMA_STORE) {
@@ -180,13 +179,14 @@ struct MarchStream {
   }
 };
 
-// One plane for an interior column.  PH = seq % 3 is a compile-time phase, so the rolling window {old, mid, new}
-// is a renaming of three register sets.  Order inside one iteration:
-//   load plane ip, F_0 / L_0 (registers)  ->  update plane ip-1 (reads scratch of plane ip-1, written last iteration)
-//   ->  F_1, F_2, L_1, L_2 of plane ip into the other scratch buffer  ->  group barrier  ->  drain the updated plane.
+// Plane IP (compile-time, 0..P+1) of the current patch for an interior column.  The rolling window {old, mid, new} along
+// axis 0 is a renaming of three register sets (IP % 3), scratch / staging buffers alternate with IP % 2, and every
+// "is this a halo plane / the last plane" decision is resolved at compile time.  Order inside one iteration:
+//   load plane IP, F_0 / L_0 (registers)  ->  update plane IP-1 (reads scratch of plane IP-1, written last iteration)
+//   ->  F_1, F_2, L_1, L_2 of plane IP into the other scratch buffer  ->  group barrier  ->  drain the updated plane.
 // The scratch buffer written here was last read before the previous barrier, so two buffers and one barrier per plane
-// are enough.
-template <class C, int PH>
+// are enough.  Nothing of the window survives a patch boundary (planes 0 and 1 never read `old`).
+template <class C, int IP>
 __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell, int sj, int sk, int st,
                                                     typename C::T (&q)[3][C::NV], typename C::T (&fi)[3][C::NR],
                                                     typename C::T (&li)[3], typename C::T (&lj)[3],
@@ -197,15 +197,11 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   using Upd = typename C::Upd;
   using Bits = typename FloatBits<T>::type;
   constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, S = C::S;
-  constexpr int NEW = PH, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
-  const int ip = ms.ip;
-  const int wb = ms.seq & 1;                 // scratch / staging buffer of this iteration
-  T* __restrict__ const FjW = ms.Fj + wb * (NR * SJ);
-  T* __restrict__ const FkW = ms.Fk + wb * (NR * SK);
-  const T* __restrict__ const FjR = ms.Fj + (wb ^ 1) * (NR * SJ);
-  const T* __restrict__ const FkR = ms.Fk + (wb ^ 1) * (NR * SK);
+  constexpr int NEW = IP % 3, MID = (IP + 2) % 3, OLD = (IP + 1) % 3;
+  constexpr int WB = IP & 1, RB = WB ^ 1;    // scratch / staging buffer written / read in this iteration
+  constexpr bool INNER = (IP >= 1 && IP <= C::P), UPDATE = (IP >= 2), LAST = (IP == C::NPL - 1);
 
-  // ------------------------------------------------------------ plane ip: state, F_0, L_0 into the window
+  // ------------------------------------------------------------ plane IP: state, F_0, L_0 into the window
   const T* __restrict__ qs = ms.wait_plane();
 #pragma unroll
   for (int v = 0; v < NV; ++v) q[NEW][v] = qs[cell * NV + v];
@@ -213,9 +209,11 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   Phys::template flux<0, T>(q[NEW], pr, fi[NEW]);
   li[NEW] = Phys::template eigen<0, T>(q[NEW], pr);
 
-  // ------------------------------------------------------------ update plane ip-1 (needs F_0 of planes ip-2 and ip)
-  if (ip >= 2) {
-    const T* __restrict__ qm = ms.previous_plane();      // plane ip-1: the neighbours' Q for the dissipation
+  // ------------------------------------------------------------ update plane IP-1 (needs F_0 of planes IP-2 and IP)
+  if constexpr (UPDATE) {
+    const T* __restrict__ qm = ms.previous_plane();      // plane IP-1: the neighbours' Q for the dissipation
+    const T* __restrict__ FjR = ms.Fj + RB * (NR * SJ);
+    const T* __restrict__ FkR = ms.Fk + RB * (NR * SK);
     const T dt = ms.dt;
     T qc[NV];
 #pragma unroll
@@ -232,68 +230,84 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
     for (int v = 0; v < C::DV; ++v)
       qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q[OLD][v], li[MID], li[NEW], li[OLD], dt);
     {
-      const T* __restrict__ LjR = ms.Lj + (wb ^ 1) * SJ;
-      const T l_plus = LjR[sj + PJ], l_minus = LjR[sj - PJ];
+      const T l_plus = ms.Lj[RB * SJ + sj + PJ], l_minus = ms.Lj[RB * SJ + sj - PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + S) * NV + v], qm[(cell - S) * NV + v], lj[MID], l_plus,
                                  l_minus, dt);
     }
     {
-      const T* __restrict__ LkR = ms.Lk + (wb ^ 1) * SK;
-      const T l_plus = LkR[sk + 1], l_minus = LkR[sk - 1];
+      const T l_plus = ms.Lk[RB * SK + sk + 1], l_minus = ms.Lk[RB * SK + sk - 1];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[MID], l_plus,
                                  l_minus, dt);
     }
-    T* dst = ms.stage + wb * (C::STAGE_SEGS * C::SEG_PITCH) + st;
+    T* dst = ms.stage + WB * (C::STAGE_SEGS * C::SEG_PITCH) + st;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = qc[v];
     if (C::USE_TMA_STORE) fence_proxy_async_smem();
   }
 
-  // ------------------------------------------------------------ plane ip: F_1, F_2, L_1, L_2 for the neighbours
-  if (ip >= 1 && ip <= C::P) {
+  // ------------------------------------------------------------ plane IP: F_1, F_2, L_1, L_2 for the neighbours
+  if constexpr (INNER) {
+    T* __restrict__ FjW = ms.Fj + WB * (NR * SJ);
+    T* __restrict__ FkW = ms.Fk + WB * (NR * SK);
     T F[NR];
     Phys::template flux<1, T>(q[NEW], pr, F);
 #pragma unroll
     for (int v = 0; v < NR; ++v) FjW[v * SJ + sj] = F[v];
     lj[NEW] = Phys::template eigen<1, T>(q[NEW], pr);
-    ms.Lj[wb * SJ + sj] = lj[NEW];
+    ms.Lj[WB * SJ + sj] = lj[NEW];
     Phys::template flux<2, T>(q[NEW], pr, F);
 #pragma unroll
     for (int v = 0; v < NR; ++v) FkW[v * SK + sk] = F[v];
     lk[NEW] = Phys::template eigen<2, T>(q[NEW], pr);
-    ms.Lk[wb * SK + sk] = lk[NEW];
+    ms.Lk[WB * SK + sk] = lk[NEW];
     lam_local = fv_max(lam_local, fv_max(li[NEW], fv_max(lj[NEW], lk[NEW])));
   }
   // per-patch maximum eigenvalue over interior cells of the input state: complete at the patch's last plane
-  const bool last_plane = (ip == C::NPL - 1);
-  if (last_plane) {
+  if constexpr (LAST) {
     T m = lam_local;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((ms.gt & 31) == 0) atomicMax(&ms.lam_slot[ms.pi & 1], FloatBits<T>::to(m));
     lam_local = T(0);
   }
-  if (C::USE_TMA_STORE && ms.gt == 0) tma_store_wait_read();   // the other staging buffer is free for the next iteration
+  if (C::USE_TMA_STORE && UPDATE && ms.gt == 0) tma_store_wait_read();   // the other staging buffer is free again
   named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
 
   // ------------------------------------------------------------ drain, prefetch, publish
-  if (ip >= 2) ms.drain_staged_plane(C::FACE_BASE);
+  if constexpr (UPDATE) ms.drain_staged_plane(IP - 2, WB, C::FACE_BASE);
   if (ms.gt == 0) {
-    // plane seq-1 was last read by the update above: its ring slot takes plane seq-1+R
-    if (ms.seq >= 1 && ms.p_seq < ms.n_seq) ms.issue_next_load();
-    if (last_plane) {
+    // the previous plane of the stream was last read by the update above: its ring slot takes the next plane to request
+    if ((IP >= 1 || ms.pi >= 1) && ms.p_seq < ms.n_seq) ms.issue_next_load();
+    if constexpr (LAST) {
       const Bits b = ms.lam_slot[ms.pi & 1];
       ms.lam_slot[ms.pi & 1] = 0;                           // next used two patches from now
       if (ms.lambda_patch) ms.lambda_patch[ms.g_index + (long long)ms.pi * ms.n_groups] = FloatBits<T>::from(b);
       group_lam = (b > group_lam) ? b : group_lam;
     }
   }
-  ms.advance();
+  ms.advance_plane();
 }
+
+// all planes of one patch, unrolled
+template <class C, int IP>
+struct MarchPatch {
+  template <class... A>
+  static __device__ __forceinline__ void interior(A&... a) {
+    march_interior_step<C, IP>(a...);
+    MarchPatch<C, IP + 1>::interior(a...);
+  }
+  static __device__ __forceinline__ void face(MarchStream<C>& ms, bool live, int f_axis, int cell, int slot_in_scratch);
+};
+template <class C>
+struct MarchPatch<C, C::P + 2> {
+  template <class... A>
+  static __device__ __forceinline__ void interior(A&...) {}
+  static __device__ __forceinline__ void face(MarchStream<C>&, bool, int, int, int) {}
+};
 
 // One plane for a face-halo column of axis AXIS (1 or 2): F_AXIS and L_AXIS of the cell one layer outside the interior.
 template <class C, int AXIS>
@@ -313,6 +327,21 @@ __device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const 
 #pragma unroll
   for (int v = 0; v < C::NR; ++v) Fs[(buf * C::NR + v) * SX + slot_in_scratch] = F[v];
   Ls[buf * SX + slot_in_scratch] = Phys::template eigen<AXIS, T>(q, pr);
+}
+
+template <class C, int IP>
+__device__ __forceinline__ void MarchPatch<C, IP>::face(MarchStream<C>& ms, bool live, int f_axis, int cell,
+                                                        int slot_in_scratch) {
+  if constexpr (IP >= 1 && IP <= C::P) {       // halo planes need no axis-1/2 fluxes: the face warps do not even wait for them
+    const typename C::T* __restrict__ qs = ms.wait_plane();
+    if (live) {
+      if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, IP & 1);
+      else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, IP & 1);
+    }
+  }
+  named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+  ms.advance_plane();
+  MarchPatch<C, IP + 1>::face(ms, live, f_axis, cell, slot_in_scratch);
 }
 
 template <class C>
@@ -353,7 +382,8 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   ms.g_index = (long long)blockIdx.x * C::NG + group;
   const long long my_patches = (n_patches > ms.g_index) ? (n_patches - ms.g_index + ms.n_groups - 1) / ms.n_groups : 0;
   ms.n_seq = (int)(my_patches * NPL);
-  ms.seq = ms.ip = ms.pi = ms.slot = 0;
+  ms.n_my_patches = (int)my_patches;
+  ms.pi = ms.slot = 0;
   ms.parity = 0;
   ms.p_seq = ms.p_ip = ms.p_pi = ms.p_slot = 0;
   if (gt == 0)
@@ -381,14 +411,8 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     Bits group_lam = 0;
     // lanes past N_INT (patch sizes whose P*P is not a multiple of 32) recompute column (0,0) and write the same
     // values to the same places as lane 0: harmless, and it keeps every warp whole for the shuffles and barriers
-    while (true) {
-      if (ms.seq >= ms.n_seq) break;
-      march_interior_step<C, 0>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
-      if (ms.seq >= ms.n_seq) break;
-      march_interior_step<C, 1>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
-      if (ms.seq >= ms.n_seq) break;
-      march_interior_step<C, 2>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
-    }
+    for (; ms.pi < ms.n_my_patches; ++ms.pi)
+      MarchPatch<C, 0>::interior(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
     if (gt == 0) {
       if (C::USE_TMA_STORE) tma_store_wait_all();
       if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
@@ -405,15 +429,7 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     const int cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
     const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos
                                               : f_pos * C::PK + (f_side ? P + 1 : 0);
-    while (ms.seq < ms.n_seq) {
-      const T* __restrict__ qs = ms.wait_plane();
-      if (live && ms.ip >= 1 && ms.ip <= P) {
-        if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, ms.seq & 1);
-        else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, ms.seq & 1);
-      }
-      named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
-      ms.advance();
-    }
+    for (; ms.pi < ms.n_my_patches; ++ms.pi) MarchPatch<C, 0>::face(ms, live, f_axis, cell, slot_in_scratch);
   }
 }
 
