@@ -179,15 +179,21 @@ struct MarchStream {
   }
 };
 
-// Plane IP (compile-time, 0..P+1) of the current patch for an interior column.  The rolling window {old, mid, new} along
-// axis 0 is a renaming of three register sets (IP % 3), scratch / staging buffers alternate with IP % 2, and every
-// "is this a halo plane / the last plane" decision is resolved at compile time.  Order inside one iteration:
-//   load plane IP, F_0 / L_0 (registers)  ->  update plane IP-1 (reads scratch of plane IP-1, written last iteration)
-//   ->  F_1, F_2, L_1, L_2 of plane IP into the other scratch buffer  ->  group barrier  ->  drain the updated plane.
+// One plane of the current patch for an interior column.  Compile-time: the phase PH = ip % 3 of the rolling window
+// {old, mid, new} along axis 0 (a renaming of three register sets) and the KIND of plane -- first (halo), second (first
+// interior plane: nothing to update yet), middle, last (halo: update only, publish the patch's eigenvalue).  Run-time:
+// the plane index ip of middle planes and the scratch / staging buffer parity ip & 1.  Six bodies exist per kernel
+// (first, second, 3 x middle, last), small enough to stay in the instruction cache with five groups at different
+// places of the loop (a fully unrolled patch, 10 bodies, stalled on instruction fetch: profiles/r01_march_v3).
+// Order inside one iteration:
+//   load plane ip, F_0 / L_0 (registers)  ->  update plane ip-1 (reads scratch of plane ip-1, written last iteration)
+//   ->  F_1, F_2, L_1, L_2 of plane ip into the other scratch buffer  ->  group barrier  ->  drain the updated plane.
 // The scratch buffer written here was last read before the previous barrier, so two buffers and one barrier per plane
 // are enough.  Nothing of the window survives a patch boundary (planes 0 and 1 never read `old`).
-template <class C, int IP>
-__device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell, int sj, int sk, int st,
+enum { MARCH_FIRST = 0, MARCH_SECOND = 1, MARCH_MIDDLE = 2, MARCH_LAST = 3 };
+
+template <class C, int PH, int KIND>
+__device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int ip, int cell, int sj, int sk, int st,
                                                     typename C::T (&q)[3][C::NV], typename C::T (&fi)[3][C::NR],
                                                     typename C::T (&li)[3], typename C::T (&lj)[3],
                                                     typename C::T (&lk)[3], typename C::T& lam_local,
@@ -197,11 +203,12 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   using Upd = typename C::Upd;
   using Bits = typename FloatBits<T>::type;
   constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, S = C::S;
-  constexpr int NEW = IP % 3, MID = (IP + 2) % 3, OLD = (IP + 1) % 3;
-  constexpr int WB = IP & 1, RB = WB ^ 1;    // scratch / staging buffer written / read in this iteration
-  constexpr bool INNER = (IP >= 1 && IP <= C::P), UPDATE = (IP >= 2), LAST = (IP == C::NPL - 1);
+  constexpr int NEW = PH % 3, MID = (PH + 2) % 3, OLD = (PH + 1) % 3;
+  constexpr bool INNER = (KIND == MARCH_SECOND || KIND == MARCH_MIDDLE), UPDATE = (KIND >= MARCH_MIDDLE),
+                 LAST = (KIND == MARCH_LAST);
+  const int wb = ip & 1, rb = wb ^ 1;        // scratch / staging buffer written / read in this iteration
 
-  // ------------------------------------------------------------ plane IP: state, F_0, L_0 into the window
+  // ------------------------------------------------------------ plane ip: state, F_0, L_0 into the window
   const T* __restrict__ qs = ms.wait_plane();
 #pragma unroll
   for (int v = 0; v < NV; ++v) q[NEW][v] = qs[cell * NV + v];
@@ -209,11 +216,13 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   Phys::template flux<0, T>(q[NEW], pr, fi[NEW]);
   li[NEW] = Phys::template eigen<0, T>(q[NEW], pr);
 
-  // ------------------------------------------------------------ update plane IP-1 (needs F_0 of planes IP-2 and IP)
+  // ------------------------------------------------------------ update plane ip-1 (needs F_0 of planes ip-2 and ip)
   if constexpr (UPDATE) {
-    const T* __restrict__ qm = ms.previous_plane();      // plane IP-1: the neighbours' Q for the dissipation
-    const T* __restrict__ FjR = ms.Fj + RB * (NR * SJ);
-    const T* __restrict__ FkR = ms.Fk + RB * (NR * SK);
+    const T* __restrict__ qm = ms.previous_plane();      // plane ip-1: the neighbours' Q for the dissipation
+    const T* __restrict__ FjR = ms.Fj + rb * (NR * SJ) + sj;
+    const T* __restrict__ FkR = ms.Fk + rb * (NR * SK) + sk;
+    const T* __restrict__ LjR = ms.Lj + rb * SJ + sj;
+    const T* __restrict__ LkR = ms.Lk + rb * SK + sk;
     const T dt = ms.dt;
     T qc[NV];
 #pragma unroll
@@ -222,48 +231,48 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
 #pragma unroll
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], fi[NEW][v], fi[OLD][v]);
 #pragma unroll
-    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FjR[v * SJ + sj + PJ], FjR[v * SJ + sj - PJ]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FjR[v * SJ + PJ], FjR[v * SJ - PJ]);
 #pragma unroll
-    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + sk + 1], FkR[v * SK + sk - 1]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + 1], FkR[v * SK - 1]);
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
 #pragma unroll
     for (int v = 0; v < C::DV; ++v)
       qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q[OLD][v], li[MID], li[NEW], li[OLD], dt);
     {
-      const T l_plus = ms.Lj[RB * SJ + sj + PJ], l_minus = ms.Lj[RB * SJ + sj - PJ];
+      const T l_plus = LjR[PJ], l_minus = LjR[-PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + S) * NV + v], qm[(cell - S) * NV + v], lj[MID], l_plus,
                                  l_minus, dt);
     }
     {
-      const T l_plus = ms.Lk[RB * SK + sk + 1], l_minus = ms.Lk[RB * SK + sk - 1];
+      const T l_plus = LkR[1], l_minus = LkR[-1];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[MID], l_plus,
                                  l_minus, dt);
     }
-    T* dst = ms.stage + WB * (C::STAGE_SEGS * C::SEG_PITCH) + st;
+    T* dst = ms.stage + wb * (C::STAGE_SEGS * C::SEG_PITCH) + st;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = qc[v];
     if (C::USE_TMA_STORE) fence_proxy_async_smem();
   }
 
-  // ------------------------------------------------------------ plane IP: F_1, F_2, L_1, L_2 for the neighbours
+  // ------------------------------------------------------------ plane ip: F_1, F_2, L_1, L_2 for the neighbours
   if constexpr (INNER) {
-    T* __restrict__ FjW = ms.Fj + WB * (NR * SJ);
-    T* __restrict__ FkW = ms.Fk + WB * (NR * SK);
+    T* __restrict__ FjW = ms.Fj + wb * (NR * SJ) + sj;
+    T* __restrict__ FkW = ms.Fk + wb * (NR * SK) + sk;
     T F[NR];
     Phys::template flux<1, T>(q[NEW], pr, F);
 #pragma unroll
-    for (int v = 0; v < NR; ++v) FjW[v * SJ + sj] = F[v];
+    for (int v = 0; v < NR; ++v) FjW[v * SJ] = F[v];
     lj[NEW] = Phys::template eigen<1, T>(q[NEW], pr);
-    ms.Lj[WB * SJ + sj] = lj[NEW];
+    ms.Lj[wb * SJ + sj] = lj[NEW];
     Phys::template flux<2, T>(q[NEW], pr, F);
 #pragma unroll
-    for (int v = 0; v < NR; ++v) FkW[v * SK + sk] = F[v];
+    for (int v = 0; v < NR; ++v) FkW[v * SK] = F[v];
     lk[NEW] = Phys::template eigen<2, T>(q[NEW], pr);
-    ms.Lk[WB * SK + sk] = lk[NEW];
+    ms.Lk[wb * SK + sk] = lk[NEW];
     lam_local = fv_max(lam_local, fv_max(li[NEW], fv_max(lj[NEW], lk[NEW])));
   }
   // per-patch maximum eigenvalue over interior cells of the input state: complete at the patch's last plane
@@ -278,10 +287,10 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
 
   // ------------------------------------------------------------ drain, prefetch, publish
-  if constexpr (UPDATE) ms.drain_staged_plane(IP - 2, WB, C::FACE_BASE);
+  if constexpr (UPDATE) ms.drain_staged_plane(ip - 2, wb, C::FACE_BASE);
   if (ms.gt == 0) {
     // the previous plane of the stream was last read by the update above: its ring slot takes the next plane to request
-    if ((IP >= 1 || ms.pi >= 1) && ms.p_seq < ms.n_seq) ms.issue_next_load();
+    if ((KIND != MARCH_FIRST || ms.pi >= 1) && ms.p_seq < ms.n_seq) ms.issue_next_load();
     if constexpr (LAST) {
       const Bits b = ms.lam_slot[ms.pi & 1];
       ms.lam_slot[ms.pi & 1] = 0;                           // next used two patches from now
@@ -292,22 +301,24 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int cell
   ms.advance_plane();
 }
 
-// all planes of one patch, unrolled
-template <class C, int IP>
-struct MarchPatch {
-  template <class... A>
-  static __device__ __forceinline__ void interior(A&... a) {
-    march_interior_step<C, IP>(a...);
-    MarchPatch<C, IP + 1>::interior(a...);
+// all planes of one patch for an interior column: first, second, middle planes 2..P (three phases in rotation), last
+template <class C, class... A>
+__device__ __forceinline__ void march_interior_patch(MarchStream<C>& ms, A&... a) {
+  march_interior_step<C, 0, MARCH_FIRST>(ms, 0, a...);
+  march_interior_step<C, 1, MARCH_SECOND>(ms, 1, a...);
+  if constexpr (C::P >= 2) {
+    int ip = 2;
+    while (true) {
+      march_interior_step<C, 2, MARCH_MIDDLE>(ms, ip, a...);
+      if (++ip > C::P) break;
+      march_interior_step<C, 0, MARCH_MIDDLE>(ms, ip, a...);
+      if (++ip > C::P) break;
+      march_interior_step<C, 1, MARCH_MIDDLE>(ms, ip, a...);
+      if (++ip > C::P) break;
+    }
   }
-  static __device__ __forceinline__ void face(MarchStream<C>& ms, bool live, int f_axis, int cell, int slot_in_scratch);
-};
-template <class C>
-struct MarchPatch<C, C::P + 2> {
-  template <class... A>
-  static __device__ __forceinline__ void interior(A&...) {}
-  static __device__ __forceinline__ void face(MarchStream<C>&, bool, int, int, int) {}
-};
+  march_interior_step<C, (C::P + 1) % 3, MARCH_LAST>(ms, C::P + 1, a...);
+}
 
 // One plane for a face-halo column of axis AXIS (1 or 2): F_AXIS and L_AXIS of the cell one layer outside the interior.
 template <class C, int AXIS>
@@ -327,21 +338,6 @@ __device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const 
 #pragma unroll
   for (int v = 0; v < C::NR; ++v) Fs[(buf * C::NR + v) * SX + slot_in_scratch] = F[v];
   Ls[buf * SX + slot_in_scratch] = Phys::template eigen<AXIS, T>(q, pr);
-}
-
-template <class C, int IP>
-__device__ __forceinline__ void MarchPatch<C, IP>::face(MarchStream<C>& ms, bool live, int f_axis, int cell,
-                                                        int slot_in_scratch) {
-  if constexpr (IP >= 1 && IP <= C::P) {       // halo planes need no axis-1/2 fluxes: the face warps do not even wait for them
-    const typename C::T* __restrict__ qs = ms.wait_plane();
-    if (live) {
-      if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, IP & 1);
-      else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, IP & 1);
-    }
-  }
-  named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
-  ms.advance_plane();
-  MarchPatch<C, IP + 1>::face(ms, live, f_axis, cell, slot_in_scratch);
 }
 
 template <class C>
@@ -412,7 +408,7 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     // lanes past N_INT (patch sizes whose P*P is not a multiple of 32) recompute column (0,0) and write the same
     // values to the same places as lane 0: harmless, and it keeps every warp whole for the shuffles and barriers
     for (; ms.pi < ms.n_my_patches; ++ms.pi)
-      MarchPatch<C, 0>::interior(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
+      march_interior_patch<C>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
     if (gt == 0) {
       if (C::USE_TMA_STORE) tma_store_wait_all();
       if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
@@ -429,7 +425,19 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     const int cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
     const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos
                                               : f_pos * C::PK + (f_side ? P + 1 : 0);
-    for (; ms.pi < ms.n_my_patches; ++ms.pi) MarchPatch<C, 0>::face(ms, live, f_axis, cell, slot_in_scratch);
+    for (; ms.pi < ms.n_my_patches; ++ms.pi) {
+      for (int ip = 0; ip < NPL; ++ip) {
+        if (ip >= 1 && ip <= P) {          // halo planes need no axis-1/2 fluxes: the face warps do not even wait for them
+          const T* __restrict__ qs = ms.wait_plane();
+          if (live) {
+            if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, ip & 1);
+            else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, ip & 1);
+          }
+        }
+        named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
+        ms.advance_plane();
+      }
+    }
   }
 }
 
