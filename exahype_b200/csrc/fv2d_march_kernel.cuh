@@ -1,0 +1,362 @@
+// sm_100a row-marching kernel for the 2-D batched stateless FV Rusanov patch update.
+//
+// Same arithmetic, statement order and results as fv_patch_kernel.cuh (reference "Unit test/test.cpp":11-104 with the
+// loop ranges of exahype/printers/CPPPrinter.py:116-137), different data flow.  The thread-per-cell kernel stages the
+// whole tile, F_n / L_n of both axes, a stash of Q and the output in shared memory and is bound by shared-memory
+// wavefronts (profiles/r01_ncu_c2_cell.txt: 85 % L1 data pipe at 46 % DRAM).  Here a WARP owns 32/P patches and marches
+// through their rows along axis 0 (the slow index `i`); nothing is staged:
+//
+//   * lane <-> (patch of the warp, interior column k).  A row of P cells of one patch is one contiguous run of the AoS
+//     batch, a cell of 4 fp64 variables is exactly one 32-byte sector: every lane loads ITS cell straight from HBM into
+//     registers with one 256-bit load (LDG.E.256, or 128-bit loads when the buffers are only 16-byte aligned) and stores
+//     its updated cell with one 256-bit store.  Loads run PF = 2 rows ahead of the row being consumed.
+//   * the axis-0 stencil lives in registers: rolling window {r-2, r-1, r} of the cell state, F_0 and L_0 (ring of 4 rows,
+//     row loop unrolled by 4 so every ring index is a compile-time constant).
+//   * only F_1, L_1 and the DV dissipated variables of the row cross lanes, through a warp-private double-buffered
+//     shared row (conflict-free SoA, one __syncwarp per row; no CTA barriers, no mbarriers, no named barriers).
+//   * the 2*P face-halo cells of axis 1 of each patch (one layer left and right of every interior row) are evaluated
+//     32 at a time before the march (lane <-> (patch, row)) into a warp-private table that the edge lanes read instead
+//     of the shared row.  Halo corners are never touched (they are not inputs).
+//   * per-patch max eigenvalue: running maximum in registers, segmented warp-shuffle reduction at the end of the patch.
+//
+// Shared memory: COMPS * 128 values per warp (6 KB for Euler fp64 var0), registers ~100: ~16-20 independent warps per SM,
+// each streaming rows of 512-1024 contiguous bytes.
+#pragma once
+
+#include "fv_patch_kernel.cuh"
+
+namespace exahype {
+
+template <class Phys_, class Upd_, typename T_, int P_, int H_, int WPC_, int MINB_, bool DISS_ALL_, bool UNHALOED_,
+          int VEC_>
+struct Fv2dMarchConfig {
+  using Phys = Phys_;
+  using Upd = Upd_;
+  using T = T_;
+  static constexpr int DIM = 2, P = P_, H = H_, WPC = WPC_, MINB = MINB_, VEC = VEC_;
+  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_;
+  static_assert(P >= 1 && P <= 32 && 32 % P == 0, "row marching needs a patch side that divides the warp");
+  static_assert(H >= 1 && WPC >= 1 && WPC <= 32, "march geometry");
+
+  static constexpr int NR = Phys::NR, NA = Phys::NA, NV = NR + NA;
+  static constexpr int S = P + 2 * H;
+  static constexpr int PPW = 32 / P;                      // patches per warp
+  static constexpr int NROW = P + 2;                      // rows a patch needs: one halo layer each side
+  static constexpr int CELL_BYTES = NV * (int)sizeof(T);
+  static constexpr int PATCH_ELEMS = S * S * NV;
+  static constexpr int OUT_PATCH_ELEMS = P * P * NV;
+  static constexpr int DV = DISS_ALL ? NR : 1;
+  static constexpr int COMPS = NR + 1 + DV;               // F_1[NR], L_1, Q[DV] cross lanes
+  static constexpr int NT = WPC * 32;
+  static_assert(VEC == 32 || VEC == 16 || VEC == (int)sizeof(T), "vector width of the global accesses");
+  static_assert(VEC == (int)sizeof(T) || CELL_BYTES % VEC == 0, "a cell must be a whole number of vectors");
+
+  // warp-private exchange area: [COMPS][XS] values; slots [0,32) row buffer 0, [32,64) row buffer 1,
+  // [64,96) left face-halo table (patch of the warp, row), [96,128) right face-halo table
+  static constexpr int XS = 128;
+  static constexpr int WARP_BYTES = COMPS * XS * (int)sizeof(T);
+  static constexpr int SMEM_BYTES = WPC * WARP_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "exchange area does not fit");
+};
+
+// one cell (NV values) between global memory and registers, VEC bytes per instruction
+template <class C>
+__device__ __forceinline__ void load_cell(const typename C::T* p, typename C::T (&q)[C::NV]) {
+  using T = typename C::T;
+  if constexpr (C::VEC == 32 && sizeof(T) == 8) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 4)
+      asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                   : "=d"(q[v]), "=d"(q[v + 1]), "=d"(q[v + 2]), "=d"(q[v + 3]) : "l"(p + v));
+  } else if constexpr (C::VEC == 32 && sizeof(T) == 4) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 8)
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(q[v]), "=f"(q[v + 1]), "=f"(q[v + 2]), "=f"(q[v + 3]), "=f"(q[v + 4]), "=f"(q[v + 5]),
+                     "=f"(q[v + 6]), "=f"(q[v + 7]) : "l"(p + v));
+  } else if constexpr (C::VEC == 16 && sizeof(T) == 8) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 2)
+      asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(q[v]), "=d"(q[v + 1]) : "l"(p + v));
+  } else if constexpr (C::VEC == 16 && sizeof(T) == 4) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 4)
+      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(q[v]), "=f"(q[v + 1]), "=f"(q[v + 2]), "=f"(q[v + 3]) : "l"(p + v));
+  } else {
+#pragma unroll
+    for (int v = 0; v < C::NV; ++v) q[v] = *reinterpret_cast<const volatile T*>(p + v);
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void store_cell(typename C::T* p, const typename C::T (&q)[C::NV]) {
+  using T = typename C::T;
+  if constexpr (C::VEC == 32 && sizeof(T) == 8) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 4)
+      asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + v), "d"(q[v]), "d"(q[v + 1]), "d"(q[v + 2]),
+                   "d"(q[v + 3]) : "memory");
+  } else if constexpr (C::VEC == 32 && sizeof(T) == 4) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 8)
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + v), "f"(q[v]), "f"(q[v + 1]),
+                   "f"(q[v + 2]), "f"(q[v + 3]), "f"(q[v + 4]), "f"(q[v + 5]), "f"(q[v + 6]), "f"(q[v + 7]) : "memory");
+  } else if constexpr (C::VEC == 16 && sizeof(T) == 8) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 2)
+      asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p + v), "d"(q[v]), "d"(q[v + 1]) : "memory");
+  } else if constexpr (C::VEC == 16 && sizeof(T) == 4) {
+#pragma unroll
+    for (int v = 0; v < C::NV; v += 4)
+      asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + v), "f"(q[v]), "f"(q[v + 1]), "f"(q[v + 2]),
+                   "f"(q[v + 3]) : "memory");
+  } else {
+#pragma unroll
+    for (int v = 0; v < C::NV; ++v) p[v] = q[v];
+  }
+}
+
+// Per-lane state of the march.  Ring index = row & 3 (compile-time in the unrolled loop).
+template <class C>
+struct RowMarch {
+  using T = typename C::T;
+  const T* row_ptr;          // this lane's cell in marching row 0 (haloed i = H-1, j = k+H) of its patch
+  T* out_ptr;                // this lane's cell in interior row 0 of the output
+  T* X;                      // warp-private exchange area [COMPS][XS]
+  T dt;
+  int lane, k;
+  int halo_slot_left, halo_slot_right;   // 64 + sub*P, 96 + sub*P (+ interior row)
+  bool store_ok;
+};
+
+// One row of the march.  SLOT = r & 3 at compile time; r itself is a run-time (warp-uniform) value.
+//   r = 0        halo row:  F_0, L_0 only
+//   r = 1        first interior row: publish F_1 / L_1 / Q for the neighbours, nothing to update yet
+//   r = 2..P     publish, and update row r-1 (needs F_0 of rows r-2 and r, neighbours of row r-1 published last step)
+//   r = P+1      halo row:  F_0, L_0, update row P
+template <class C, int SLOT>
+__device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename C::T (&q)[4][C::NV],
+                                          typename C::T (&f0)[4][C::NR], typename C::T (&l0)[4],
+                                          typename C::T& l1_mid, typename C::T (&q_old)[C::DV],
+                                          typename C::T& lam_local) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  using Upd = typename C::Upd;
+  constexpr int NV = C::NV, NR = C::NR, DV = C::DV, XS = C::XS, P = C::P;
+  constexpr int NEW = SLOT, MID = (SLOT + 3) & 3, OLD = (SLOT + 2) & 3, PRE = (SLOT + 2) & 3;
+
+  // row r+2 -> the ring slot that held row r-2 (whose dissipated variables were saved to q_old last step)
+  if (r + 2 < C::NROW) load_cell<C>(m.row_ptr + (long long)(r + 2) * (C::S * NV), q[PRE]);
+
+  const auto pr = Phys::template prims<T>(q[NEW]);
+  Phys::template flux<0, T>(q[NEW], pr, f0[NEW]);
+  l0[NEW] = Phys::template eigen<0, T>(q[NEW], pr);
+
+  const bool inner = (r >= 1) && (r <= P);
+  T f1[NR], l1_new = T(0);
+  if (inner) {
+    Phys::template flux<1, T>(q[NEW], pr, f1);
+    l1_new = Phys::template eigen<1, T>(q[NEW], pr);
+    lam_local = fv_max(lam_local, fv_max(l0[NEW], l1_new));
+  }
+
+  if (r >= 2) {
+    // ---------------------------------------------------------------- update interior row r-1
+    const int rb = (r - 1) & 1;
+    const int sl = (m.k == 0) ? (m.halo_slot_left + (r - 2)) : (rb * 32 + m.lane - 1);
+    const int sr = (m.k == P - 1) ? (m.halo_slot_right + (r - 2)) : (rb * 32 + m.lane + 1);
+    const T* __restrict__ xl = m.X + sl;
+    const T* __restrict__ xr = m.X + sr;
+    T qc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) qc[v] = q[MID][v];
+    // "Q_copy = Q_copy - 0.5*F[+1] + 0.5*F[-1]" for axis 0 then axis 1 (test.cpp:60-77)
+#pragma unroll
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], f0[NEW][v], f0[OLD][v]);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], xr[v * XS], xl[v * XS]);
+    // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0 then axis 1 (test.cpp:78-95)
+#pragma unroll
+    for (int v = 0; v < DV; ++v)
+      qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q_old[v], l0[MID], l0[NEW], l0[OLD], m.dt);
+    {
+      const T l_plus = xr[NR * XS], l_minus = xl[NR * XS];
+#pragma unroll
+      for (int v = 0; v < DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], q[MID][v], xr[(NR + 1 + v) * XS], xl[(NR + 1 + v) * XS], l1_mid, l_plus, l_minus,
+                                 m.dt);
+    }
+    if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
+  }
+
+  // row r-1 becomes row r-2 of the next step: keep what the dissipation needs of it before its ring slot is reloaded
+#pragma unroll
+  for (int v = 0; v < DV; ++v) q_old[v] = q[MID][v];
+  l1_mid = l1_new;
+
+  if (inner) {
+    // ---------------------------------------------------------------- publish row r for the neighbouring lanes
+    T* __restrict__ xw = m.X + (r & 1) * 32 + m.lane;
+#pragma unroll
+    for (int v = 0; v < NR; ++v) xw[v * XS] = f1[v];
+    xw[NR * XS] = l1_new;
+#pragma unroll
+    for (int v = 0; v < DV; ++v) xw[(NR + 1 + v) * XS] = q[NEW][v];
+  }
+  __syncwarp();
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
+                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  using Bits = typename FloatBits<T>::type;
+  constexpr int P = C::P, H = C::H, S = C::S, NV = C::NV, NR = C::NR, DV = C::DV, XS = C::XS, PPW = C::PPW;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long unit = (long long)blockIdx.x * C::WPC + warp;     // one unit = PPW consecutive patches
+  const long long first_patch = unit * PPW;
+  if (first_patch >= n_patches) return;                             // whole warp leaves together
+
+  RowMarch<C> m;
+  m.X = reinterpret_cast<T*>(smem + warp * C::WARP_BYTES);
+  m.dt = dt;
+  m.lane = lane;
+  const int sub = lane / P;
+  m.k = lane - sub * P;
+  m.halo_slot_left = 64 + sub * P;
+  m.halo_slot_right = 96 + sub * P;
+  // a ragged last unit recomputes the batch's last patch in its surplus lanes and stores nothing for them
+  long long patch = first_patch + sub;
+  m.store_ok = patch < n_patches;
+  if (!m.store_ok) patch = n_patches - 1;
+  m.row_ptr = q_in + patch * (long long)C::PATCH_ELEMS + ((long long)(H - 1) * S + (m.k + H)) * NV;
+  m.out_ptr = C::UNHALOED ? q_out + patch * (long long)C::OUT_PATCH_ELEMS + m.k * NV
+                          : q_out + patch * (long long)C::PATCH_ELEMS + ((long long)H * S + (m.k + H)) * NV;
+
+  T q[4][NV], f0[4][NR], l0[4], l1_mid = T(0), q_old[DV], lam_local = T(0);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) q[w][v] = T(0);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) f0[w][v] = T(0);
+    l0[w] = T(0);
+  }
+#pragma unroll
+  for (int v = 0; v < DV; ++v) q_old[v] = T(0);
+
+  // rows 0 and 1 of the march are requested first, the face-halo cells behind them
+  load_cell<C>(m.row_ptr, q[0]);
+  load_cell<C>(m.row_ptr + S * NV, q[1]);
+
+  {
+    // ------------------------------------------------------------------ face-halo table: lane <-> (patch, interior row)
+    long long hp = first_patch + sub;
+    if (hp >= n_patches) hp = n_patches - 1;
+    const T* left = q_in + hp * (long long)C::PATCH_ELEMS + ((long long)(m.k + H) * S + (H - 1)) * NV;   // row = m.k
+    T ql[NV], qr[NV];
+    load_cell<C>(left, ql);
+    load_cell<C>(left + (P + 1) * NV, qr);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const T(&qh)[NV] = side ? qr : ql;
+      const auto pr = Phys::template prims<T>(qh);
+      T F[NR];
+      Phys::template flux<1, T>(qh, pr, F);
+      T* __restrict__ xw = m.X + (side ? 96 : 64) + lane;
+#pragma unroll
+      for (int v = 0; v < NR; ++v) xw[v * XS] = F[v];
+      xw[NR * XS] = Phys::template eigen<1, T>(qh, pr);
+#pragma unroll
+      for (int v = 0; v < DV; ++v) xw[(NR + 1 + v) * XS] = qh[v];
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ the march: rows 0..P+1, ring index = row & 3
+  int r = 0;
+  while (true) {
+    march_row<C, 0>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
+    if (++r >= C::NROW) break;
+    march_row<C, 1>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
+    if (++r >= C::NROW) break;
+    march_row<C, 2>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
+    if (++r >= C::NROW) break;
+    march_row<C, 3>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
+    if (++r >= C::NROW) break;
+  }
+
+  // ------------------------------------------------------------------ max eigenvalue of the input state
+  T lam = lam_local;
+#pragma unroll
+  for (int o = P / 2; o > 0; o >>= 1) lam = fv_max(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+  if (lambda_patch != nullptr && m.k == 0 && m.store_ok) lambda_patch[patch] = lam;
+  if (lambda_max != nullptr) {
+#pragma unroll
+    for (int o = 16; o >= P && o > 0; o >>= 1) lam = fv_max(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+    if (lane == 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), FloatBits<T>::to(lam));
+  }
+}
+
+template <class C>
+struct Fv2dMarchLauncher {
+  static cudaError_t prepare(FvLaunchInfo* info, long long n_patches) {
+    static int cached_ctas_per_sm[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (cached_ctas_per_sm[dev] == 0) {
+      err = cudaFuncSetAttribute(fv2d_march_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+      if (err != cudaSuccess) return err;
+      int per_sm = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fv2d_march_kernel<C>, C::NT, C::SMEM_BYTES);
+      if (err != cudaSuccess) return err;
+      if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+      cached_ctas_per_sm[dev] = per_sm;
+    }
+    const long long units = (n_patches + C::PPW - 1) / C::PPW;
+    info->grid = (int)((units + C::WPC - 1) / C::WPC);
+    info->block = C::NT;
+    info->smem_bytes = C::SMEM_BYTES;
+    info->patches_per_tile = C::PPW * C::WPC;
+    info->ctas_per_sm = cached_ctas_per_sm[dev];
+    return cudaSuccess;
+  }
+
+  static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
+                            void* lambda_max, cudaStream_t stream) {
+    using T = typename C::T;
+    if (n_patches <= 0) return cudaSuccess;
+    FvLaunchInfo info;
+    cudaError_t err = prepare(&info, n_patches);
+    if (err != cudaSuccess) return err;
+    fv2d_march_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
+        static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max));
+    return cudaGetLastError();
+  }
+};
+
+// picks the widest vector the buffers' alignment allows: 32-byte cells on 32-byte aligned buffers -> 256-bit accesses
+template <class C32, class C16>
+struct Fv2dMarchDispatch {
+  static bool wide(const void* a, const void* b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 31) == 0;
+  }
+  static cudaError_t prepare(FvLaunchInfo* info, long long n_patches) {
+    return Fv2dMarchLauncher<C32>::prepare(info, n_patches);
+  }
+  static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
+                            void* lambda_max, cudaStream_t stream) {
+    if (wide(q_in, q_out)) return Fv2dMarchLauncher<C32>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
+    return Fv2dMarchLauncher<C16>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
+  }
+};
+
+}  // namespace exahype

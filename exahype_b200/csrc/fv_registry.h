@@ -6,6 +6,7 @@
 #include "../../include/exahype_cuda.h"
 #include "fv_patch_kernel.cuh"
 #include "fv3d_march_kernel.cuh"
+#include "fv2d_march_kernel.cuh"
 
 namespace exahype {
 
@@ -72,6 +73,44 @@ FvEntryList swe2d_entries();
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, false)>::prepare,   \
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, false, true)>::prepare,   \
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
+  }
+
+// widest global access a cell allows: 256-bit (one 32-byte sector per 4-variable fp64 cell), else 128-bit, else scalar
+template <typename T, int NV>
+struct Fv2dVec {
+  static constexpr int BYTES = NV * (int)sizeof(T);
+  static constexpr int NARROW = (BYTES % 16 == 0) ? 16 : (int)sizeof(T);
+  static constexpr int WIDE = (BYTES % 32 == 0) ? 32 : NARROW;
+};
+
+#define EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WHICH)                                            \
+  ::exahype::Fv2dMarchConfig<PHYS, ::exahype::RusanovUpdate, T, P, H, WPC, MINB, DA, UH,                       \
+                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH>
+#define EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, DA, UH)                                              \
+  ::exahype::Fv2dMarchDispatch<EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WIDE),                     \
+                               EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, NARROW)>
+
+// 2-D shape served by the row-marching kernel (WPC warps per CTA), with the thread-per-cell kernel (G, NT, MINB_CELL) as
+// alternative
+#define EXAHYPE_FV2D_ENTRY(MODEL, DTYPE, PHYS, T, P, H, WPC, MINB, G, NT, MINB_CELL)                             \
+  {                                                                                                       \
+    {MODEL, DTYPE, 2, P, H, PHYS::NR, PHYS::NA, 0u},                                                      \
+        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, false)::launch,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, false)::launch,                               \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, true)::launch,                               \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, true)::launch},                               \
+        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, false)::prepare,                             \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, false)::prepare,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, true)::prepare,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, true)::prepare},                              \
+        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, false)>::launch,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, false)>::launch,    \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, true)>::launch,    \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, true)>::launch},    \
+        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, false)>::prepare,  \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, false)>::prepare,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, true)>::prepare,   \
+         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
   }
 
 }  // namespace exahype

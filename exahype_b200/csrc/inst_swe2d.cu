@@ -1,5 +1,6 @@
 // Committed instantiations: 2-D shallow water (h, hu, hv | bathymetry), fp64 and fp32.
-// BASELINE.json config C4: 32x32 patches + 1 halo -- 1024 interior cells, two per thread.
+// BASELINE.json config C4: 32x32 patches + 1 halo -- row marching, one patch per warp (alternative: thread-per-cell,
+// 1024 interior cells, two per thread).
 #include "fv_registry.h"
 
 namespace exahype {
@@ -7,10 +8,11 @@ namespace {
 using SW = SwePhysics<3, 1>;
 
 const FvEntry kEntries[] = {
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 2, 32, 1, 1, 512, 1),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 2, 32, 1, 1, 512, 1),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 2, 16, 1, 1, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 2, 16, 1, 1, 256, 2),
+    // row-marching kernel (default): WPC warps per CTA, MINB | thread-per-cell kernel: G, NT, MINB
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 32, 1, 4, 4, 1, 512, 1),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 32, 1, 4, 4, 1, 512, 1),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 16, 1, 4, 4, 1, 256, 2),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 16, 1, 4, 4, 1, 256, 2),
 };
 }  // namespace
 
