@@ -47,7 +47,18 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB, build_dir: str = BUILD) -> str:
+    """``lib`` / ``build_dir`` / ``extra_flags`` exist for tuning experiments (a second library next to the product one)."""
+    global BUILD, LIB
+    saved = (BUILD, LIB)
+    BUILD, LIB = build_dir, lib
+    try:
+        return _build(force, verbose, extra_flags)
+    finally:
+        BUILD, LIB = saved
+
+
+def _build(force: bool, verbose: bool, extra_flags) -> str:
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
@@ -86,5 +97,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", default="", help="tuning experiment: build exahype_b200/variants/<name>/libexahype_cuda.so")
+    ap.add_argument("--flag", action="append", default=[], help="extra nvcc flag (repeatable), e.g. --flag=-DEXAHYPE_2D_PF=1")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    if a.variant:
+        d = os.path.join(HERE, "variants", a.variant)
+        print(build(force=a.force, verbose=a.verbose, extra_flags=a.flag, lib=os.path.join(d, "libexahype_cuda.so"),
+                    build_dir=os.path.join(d, "build")))
+    else:
+        print(build(force=a.force, verbose=a.verbose, extra_flags=a.flag))

@@ -28,12 +28,15 @@
 namespace exahype {
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int WPC_, int MINB_, bool DISS_ALL_, bool UNHALOED_,
-          int VEC_>
+          int VEC_, int PF_ = 2>
 struct Fv2dMarchConfig {
   using Phys = Phys_;
   using Upd = Upd_;
   using T = T_;
   static constexpr int DIM = 2, P = P_, H = H_, WPC = WPC_, MINB = MINB_, VEC = VEC_;
+  static constexpr int PF = PF_;                          // rows between a register load and its use
+  static constexpr int RING = PF + 2;                     // rows r-1, r, r+1 .. r+PF live in registers
+  static_assert(PF >= 1 && PF <= 4, "register prefetch distance");
   static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_;
   static_assert(P >= 1 && P <= 32 && 32 % P == 0, "row marching needs a patch side that divides the warp");
   static_assert(H >= 1 && WPC >= 1 && WPC <= 32, "march geometry");
@@ -48,6 +51,14 @@ struct Fv2dMarchConfig {
   static constexpr int DV = DISS_ALL ? NR : 1;
   static constexpr int COMPS = NR + 1 + DV;               // F_1[NR], L_1, Q[DV] cross lanes
   static constexpr int NT = WPC * 32;
+  static constexpr int ROW_BYTES = S * CELL_BYTES;        // one haloed row of a patch (contiguous in the AoS batch)
+  // rows are pulled into L2 ahead of the register loads by bulk prefetches (one lane per patch, no registers): the whole
+  // patch at once when it is small, else a window of ~12 KB rolling ahead of the march
+#ifndef EXAHYPE_2D_L2
+#define EXAHYPE_2D_L2 1
+#endif
+  static constexpr bool L2_BULK = EXAHYPE_2D_L2 && (ROW_BYTES % 16 == 0);
+  static constexpr int L2_ROWS = (NROW * ROW_BYTES <= 16 * 1024) ? NROW : ((12 * 1024) / ROW_BYTES < 4 ? 4 : (12 * 1024) / ROW_BYTES);
   static_assert(VEC == 32 || VEC == 16 || VEC == (int)sizeof(T), "vector width of the global accesses");
   static_assert(VEC == (int)sizeof(T) || CELL_BYTES % VEC == 0, "a cell must be a whole number of vectors");
 
@@ -117,11 +128,16 @@ __device__ __forceinline__ void store_cell(typename C::T* p, const typename C::T
   }
 }
 
-// Per-lane state of the march.  Ring index = row & 3 (compile-time in the unrolled loop).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Per-lane state of the march.  Ring index = row % RING (compile-time in the unrolled loop).
 template <class C>
 struct RowMarch {
   using T = typename C::T;
   const T* row_ptr;          // this lane's cell in marching row 0 (haloed i = H-1, j = k+H) of its patch
+  const unsigned char* l2_ptr;   // marching row 0, haloed column 0 of the patch (lanes with k == 0 prefetch)
   T* out_ptr;                // this lane's cell in interior row 0 of the output
   T* X;                      // warp-private exchange area [COMPS][XS]
   T dt;
@@ -136,18 +152,22 @@ struct RowMarch {
 //   r = 2..P     publish, and update row r-1 (needs F_0 of rows r-2 and r, neighbours of row r-1 published last step)
 //   r = P+1      halo row:  F_0, L_0, update row P
 template <class C, int SLOT>
-__device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename C::T (&q)[4][C::NV],
-                                          typename C::T (&f0)[4][C::NR], typename C::T (&l0)[4],
+__device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename C::T (&q)[C::RING][C::NV],
+                                          typename C::T (&f0)[C::RING][C::NR], typename C::T (&l0)[C::RING],
                                           typename C::T& l1_mid, typename C::T (&q_old)[C::DV],
                                           typename C::T& lam_local) {
   using T = typename C::T;
   using Phys = typename C::Phys;
   using Upd = typename C::Upd;
   constexpr int NV = C::NV, NR = C::NR, DV = C::DV, XS = C::XS, P = C::P;
-  constexpr int NEW = SLOT, MID = (SLOT + 3) & 3, OLD = (SLOT + 2) & 3, PRE = (SLOT + 2) & 3;
+  constexpr int RING = C::RING, PF = C::PF;
+  constexpr int NEW = SLOT, MID = (SLOT + RING - 1) % RING, OLD = (SLOT + RING - 2) % RING, PRE = (SLOT + PF) % RING;
+  static_assert(PRE == OLD, "the prefetched row takes the ring slot of row r-2");
 
-  // row r+2 -> the ring slot that held row r-2 (whose dissipated variables were saved to q_old last step)
-  if (r + 2 < C::NROW) load_cell<C>(m.row_ptr + (long long)(r + 2) * (C::S * NV), q[PRE]);
+  // row r+PF -> the ring slot that held row r-2 (whose dissipated variables were saved to q_old last step)
+  if (r + PF < C::NROW) load_cell<C>(m.row_ptr + (long long)(r + PF) * (C::S * NV), q[PRE]);
+  if (C::L2_BULK && C::L2_ROWS < C::NROW && m.k == 0 && r + C::L2_ROWS < C::NROW)
+    l2_prefetch_bulk(m.l2_ptr + (long long)(r + C::L2_ROWS) * C::ROW_BYTES, C::ROW_BYTES);
 
   const auto pr = Phys::template prims<T>(q[NEW]);
   Phys::template flux<0, T>(q[NEW], pr, f0[NEW]);
@@ -207,6 +227,15 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
   __syncwarp();
 }
 
+// RING consecutive rows, one body per ring slot; returns true when the patch is finished
+template <class C, int SLOT, class... A>
+__device__ __forceinline__ bool march_ring(const RowMarch<C>& m, int& r, A&... a) {
+  march_row<C, SLOT>(m, r, a...);
+  if (++r >= C::NROW) return true;
+  if constexpr (SLOT + 1 < C::RING) return march_ring<C, SLOT + 1>(m, r, a...);
+  else return false;
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
@@ -237,10 +266,12 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   m.row_ptr = q_in + patch * (long long)C::PATCH_ELEMS + ((long long)(H - 1) * S + (m.k + H)) * NV;
   m.out_ptr = C::UNHALOED ? q_out + patch * (long long)C::OUT_PATCH_ELEMS + m.k * NV
                           : q_out + patch * (long long)C::PATCH_ELEMS + ((long long)H * S + (m.k + H)) * NV;
+  m.l2_ptr = reinterpret_cast<const unsigned char*>(q_in + patch * (long long)C::PATCH_ELEMS + (long long)(H - 1) * S * NV);
+  if (C::L2_BULK && m.k == 0) l2_prefetch_bulk(m.l2_ptr, C::L2_ROWS * C::ROW_BYTES);
 
-  T q[4][NV], f0[4][NR], l0[4], l1_mid = T(0), q_old[DV], lam_local = T(0);
+  T q[C::RING][NV], f0[C::RING][NR], l0[C::RING], l1_mid = T(0), q_old[DV], lam_local = T(0);
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
+  for (int w = 0; w < C::RING; ++w) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) q[w][v] = T(0);
 #pragma unroll
@@ -250,9 +281,9 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
 #pragma unroll
   for (int v = 0; v < DV; ++v) q_old[v] = T(0);
 
-  // rows 0 and 1 of the march are requested first, the face-halo cells behind them
-  load_cell<C>(m.row_ptr, q[0]);
-  load_cell<C>(m.row_ptr + S * NV, q[1]);
+  // rows 0..PF-1 of the march are requested first, the face-halo cells behind them
+#pragma unroll
+  for (int w = 0; w < C::PF; ++w) load_cell<C>(m.row_ptr + w * (S * NV), q[w]);
 
   {
     // ------------------------------------------------------------------ face-halo table: lane <-> (patch, interior row)
@@ -278,18 +309,9 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     __syncwarp();
   }
 
-  // ------------------------------------------------------------------ the march: rows 0..P+1, ring index = row & 3
+  // ------------------------------------------------------------------ the march: rows 0..P+1, ring index = row % RING
   int r = 0;
-  while (true) {
-    march_row<C, 0>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
-    if (++r >= C::NROW) break;
-    march_row<C, 1>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
-    if (++r >= C::NROW) break;
-    march_row<C, 2>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
-    if (++r >= C::NROW) break;
-    march_row<C, 3>(m, r, q, f0, l0, l1_mid, q_old, lam_local);
-    if (++r >= C::NROW) break;
-  }
+  while (!march_ring<C, 0>(m, r, q, f0, l0, l1_mid, q_old, lam_local)) {}
 
   // ------------------------------------------------------------------ max eigenvalue of the input state
   T lam = lam_local;

@@ -83,9 +83,12 @@ struct Fv2dVec {
   static constexpr int WIDE = (BYTES % 32 == 0) ? 32 : NARROW;
 };
 
+#ifndef EXAHYPE_2D_PF
+#define EXAHYPE_2D_PF 2   // register prefetch distance of the row-marching kernel (rows)
+#endif
 #define EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WHICH)                                            \
   ::exahype::Fv2dMarchConfig<PHYS, ::exahype::RusanovUpdate, T, P, H, WPC, MINB, DA, UH,                       \
-                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH>
+                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH, EXAHYPE_2D_PF>
 #define EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, DA, UH)                                              \
   ::exahype::Fv2dMarchDispatch<EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WIDE),                     \
                                EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, NARROW)>

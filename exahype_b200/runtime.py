@@ -18,7 +18,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libexahype_cuda.so")
+# EXAHYPE_CUDA_LIB points the binding at another build of the same ABI (kernel-tuning experiments)
+LIB_PATH = os.environ.get("EXAHYPE_CUDA_LIB") or os.path.join(_HERE, "libexahype_cuda.so")
 
 MODEL = {"euler": 0, "swe": 1}
 DTYPE = {"f64": 0, "f32": 1}
