@@ -342,51 +342,11 @@ def main():
 
 
 def synthetic_on_device(torch, upd, first_patch: int, n_patches: int, tdt, device="cuda"):
-    """SplitMix64-based admissible state of SURVEY.md 8d, evaluated with torch integer ops on the device so a 1.3 GB
-    shard does not cross PCIe.  Bit-identical to oracle.fill_synthetic (tests/test_bench_input.py)."""
-    nv = upd.n_var
-    cells = n_patches * upd.side ** upd.dim
-    first_cell = first_patch * upd.side ** upd.dim
-    out = torch.empty((cells, nv), dtype=torch.float64, device=device)
-    chunk = 1 << 22
-    mask = (1 << 64) - 1
-
-    def c(x):  # two's-complement int64 constant
-        x &= mask
-        return x - (1 << 64) if x >= (1 << 63) else x
-
-    def lsr(z, s):  # logical shift right on int64
-        return (z >> s) & c((1 << (64 - s)) - 1)
-
-    for lo in range(0, cells, chunk):
-        n = min(chunk, cells - lo)
-        idx = (torch.arange(n, dtype=torch.int64, device=device).unsqueeze(1) + (first_cell + lo)) * nv \
-            + torch.arange(nv, dtype=torch.int64, device=device).unsqueeze(0)
-        z = (idx + 20240601) * c(0x9E3779B97F4A7C15)
-        z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
-        z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
-        z = z ^ lsr(z, 31)
-        u = lsr(z, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
-        o = out[lo:lo + n]
-        if upd.model == "euler":
-            d = upd.dim
-            rho = 1.0 + u[:, 0]
-            ke = torch.zeros_like(rho)
-            for k in range(d):
-                vel = u[:, 1 + k] - 0.5
-                o[:, 1 + k] = rho * vel
-                ke = ke + vel * vel
-            p = 1.0 + u[:, d + 1]
-            o[:, 0] = rho
-            o[:, d + 1] = p / (1.4 - 1.0) + 0.5 * rho * ke
-            o[:, d + 2:] = u[:, d + 2:]
-        else:
-            hgt = 1.0 + u[:, 0]
-            o[:, 0] = hgt
-            o[:, 1] = hgt * (0.2 * (u[:, 1] - 0.5))
-            o[:, 2] = hgt * (0.2 * (u[:, 2] - 0.5))
-            o[:, 3:] = 0.1 * u[:, 3:]
-    return out.to(tdt).reshape(upd.in_shape(n_patches))
+    """SplitMix64-based admissible state of SURVEY.md 8d, generated by the library's own kernel
+    (exahype_cuda_fill_synthetic) so a 1.3 GB shard does not cross PCIe.  Bit-identical to oracle.fill_synthetic
+    (tests/test_gpu_parity.py::test_device_generator_equals_oracle_fill)."""
+    q = torch.empty(upd.in_shape(n_patches), dtype=tdt, device=device)
+    return upd.fill_synthetic(q, first_patch)
 
 
 def time_variants(torch, runtime, args):

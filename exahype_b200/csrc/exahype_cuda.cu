@@ -19,6 +19,11 @@
 
 #include "fv_registry.h"
 
+namespace exahype {
+cudaError_t fill_synthetic(const exahype_fv_config* cfg, void* q, long long first_cell, long long n_cells,
+                           unsigned long long seed, cudaStream_t stream);   // synthetic.cu
+}
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -125,6 +130,22 @@ int exahype_cuda_fv_list(exahype_fv_config* out, int capacity) {
 }
 
 int64_t exahype_cuda_launch_count(void) { return g_launches.load(); }
+
+int exahype_cuda_fill_synthetic(const exahype_fv_config* cfg, void* q, int64_t first_cell, int64_t n_cells,
+                                uint64_t seed, void* stream) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (n_cells < 0 || first_cell < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "first_cell / n_cells must be >= 0");
+  if (n_cells == 0) return EXAHYPE_OK;
+  if (!q) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q must not be null");
+  const int nv = cfg->n_real + cfg->n_aux;
+  if ((cfg->model == EXAHYPE_MODEL_EULER && cfg->n_real < cfg->dim + 2) || (cfg->model == EXAHYPE_MODEL_SWE && nv < 3))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "too few variables for the model's synthetic state");
+  cudaError_t err = exahype::fill_synthetic(cfg, q, first_cell, n_cells, seed, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "fill_synthetic_kernel launch");
+  g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
 
 int exahype_cuda_fv_launch_info(const exahype_fv_config* cfg, int64_t n_patches, int* grid, int* block,
                                 int* smem_bytes, int* patches_per_tile) {

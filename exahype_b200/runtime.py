@@ -68,6 +68,7 @@ def load(path: Optional[str] = None) -> ctypes.CDLL:
     lib.exahype_cuda_time_step_host.argtypes = [c_cfg, vp, vp, i64, dbl, vp, vp]
     lib.exahype_cuda_host_pipeline_configure.argtypes = [i64, i32]
     lib.exahype_cuda_launch_count.restype = i64
+    lib.exahype_cuda_fill_synthetic.argtypes = [c_cfg, vp, i64, i64, ctypes.c_uint64, vp]
     ip = ctypes.POINTER(ctypes.c_int)
     lib.exahype_cuda_fv_launch_info.argtypes = [c_cfg, i64, ip, ip, ip, ip]
     lib.exahype_cuda_nccl_unique_id.argtypes = [vp]
@@ -239,6 +240,22 @@ class PatchUpdate:
                 lambda_patch.data_ptr() if lambda_patch is not None else None,
                 lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
         return q_out
+
+    def fill_synthetic(self, q, first_patch: int = 0, seed: int = 20240601, stream=None):
+        """Fills the CUDA tensor ``q`` (``in_shape(n)``) with the benchmark's synthetic admissible state for the global
+        patches ``first_patch .. first_patch+n``, on the device."""
+        import torch
+        n = self._n_patches(q.numel())
+        if not q.is_cuda or not q.is_contiguous() or q.dtype != (torch.float64 if self.dtype == "f64" else torch.float32):
+            raise ValueError("q must be a contiguous CUDA tensor of this object's dtype")
+        if stream is None:
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+        cells = self.side ** self.dim
+        c = self.config()
+        with torch.cuda.device(q.device):
+            check(self._lib.exahype_cuda_fill_synthetic(ctypes.byref(c), q.data_ptr(), first_patch * cells, n * cells,
+                                                        seed, stream), self._lib)
+        return q
 
     # ------------------------------------------------------------------ the reference's call shape, host memory
     def time_step(self, Q: np.ndarray, dt: float, Q_out: Optional[np.ndarray] = None, lambda_patch=None):

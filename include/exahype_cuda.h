@@ -120,6 +120,15 @@ int exahype_cuda_host_pipeline_release(void);
 /* Chunk size (patches) and number of in-flight chunks used by exahype_cuda_time_step_host; 0 keeps the default. */
 int exahype_cuda_host_pipeline_configure(int64_t chunk_patches, int depth);
 
+/*
+ * Synthetic admissible input of the benchmark generated on the device: n_cells haloed cells
+ * starting at global cell index first_cell (= first_patch * S^dim), every slot a SplitMix64 hash of its own flat index, so
+ * shards generated on different GPUs are the slices of one global batch.  New; the reference has no benchmark input.
+ */
+#define EXAHYPE_SYNTHETIC_SEED 20240601ull
+int exahype_cuda_fill_synthetic(const exahype_fv_config* cfg, void* q, int64_t first_cell, int64_t n_cells,
+                                uint64_t seed, void* stream);
+
 /* Number of kernels launched by this library in this process since load (for bench.py's gpu_launches). */
 int64_t exahype_cuda_launch_count(void);
 /* Kernel geometry picked for cfg on the current device: grid, block, dynamic smem bytes, patches per tile. */

@@ -130,6 +130,22 @@ def test_euler2d_golden_g2r(torch, rt, oracle, diss, expected):
     assert lmax == 2.1332213875447144
 
 
+@pytest.mark.parametrize("model,dim,P,nr,na,dtype", [("euler", 3, 8, 5, 0, "f64"), ("euler", 2, 16, 4, 0, "f64"),
+                                                      ("swe", 2, 32, 3, 1, "f64"), ("swe", 2, 32, 3, 1, "f32"),
+                                                      ("euler", 2, 3, 4, 0, "f64"), ("euler", 2, 4, 5, 5, "f64")])
+def test_device_generator_equals_oracle_fill(torch, rt, oracle, model, dim, P, nr, na, dtype):
+    """bench.py generates its input with exahype_cuda_fill_synthetic: it must be the oracle's synthetic state bit for
+    bit, shard by shard (so the benchmark runs on exactly the data the parity tests cover)."""
+    upd = rt.PatchUpdate(model, dim, P, 1, nr, na, dtype=dtype)
+    cfg = oracle_cfg(oracle, upd)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    npdt = np.float64 if dtype == "f64" else np.float32
+    q = torch.zeros(upd.in_shape(9), dtype=tdt, device="cuda")
+    got = upd.fill_synthetic(q, first_patch=5).cpu().numpy()
+    want = oracle.fill_synthetic(cfg, 9, dtype=npdt, first_patch=5)
+    assert_bitwise(got, want, "synthetic input")
+
+
 # ----------------------------------------------------------------------------------------- every committed shape
 def _committed():
     from exahype_b200 import runtime
