@@ -70,6 +70,14 @@ struct Fv2dMarchConfig {
   static_assert(SMEM_BYTES <= 227 * 1024, "exchange area does not fit");
 };
 
+// widest global access a cell allows: 256-bit (one 32-byte sector per 4-variable fp64 cell), else 128-bit, else scalar
+template <typename T, int NV>
+struct Fv2dVec {
+  static constexpr int BYTES = NV * (int)sizeof(T);
+  static constexpr int NARROW = (BYTES % 16 == 0) ? 16 : (int)sizeof(T);
+  static constexpr int WIDE = (BYTES % 32 == 0) ? 32 : NARROW;
+};
+
 // one cell (NV values) between global memory and registers, VEC bytes per instruction
 template <class C>
 __device__ __forceinline__ void load_cell(const typename C::T* p, typename C::T (&q)[C::NV]) {
@@ -380,5 +388,11 @@ struct Fv2dMarchDispatch {
     return Fv2dMarchLauncher<C16>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
   }
 };
+
+// what a generated unit (exahype.printers.CUDAPrinter) instantiates: 4 warps per CTA, dispatch on buffer alignment
+template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
+using Fv2dMarchAuto =
+    Fv2dMarchDispatch<Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::WIDE>,
+                      Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW>>;
 
 }  // namespace exahype

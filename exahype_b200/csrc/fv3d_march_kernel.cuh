@@ -486,4 +486,18 @@ struct Fv3dMarchLauncher {
   }
 };
 
+// what a generated unit (exahype.printers.CUDAPrinter) instantiates: as many groups per CTA as 227 KB of shared memory and
+// 128 registers per thread allow, planes through a 5-deep ring
+template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
+struct Fv3dMarchAutoConfig {
+  using One = Fv3dMarchConfig<Phys, Upd, T, P, H, 1, 5, 1, DA, UH>;
+  static constexpr int BY_SMEM = (227 * 1024) / One::GROUP_BYTES;
+  static constexpr int BY_REGS = 512 / One::GROUP_THREADS;
+  static constexpr int NG0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+  static constexpr int NG = NG0 < 1 ? 1 : (NG0 > 15 ? 15 : NG0);
+  using type = Fv3dMarchConfig<Phys, Upd, T, P, H, NG, 5, 1, DA, UH>;
+};
+template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
+using Fv3dMarchAuto = Fv3dMarchLauncher<typename Fv3dMarchAutoConfig<Phys, Upd, T, P, H, DA, UH>::type>;
+
 }  // namespace exahype

@@ -75,14 +75,6 @@ FvEntryList swe2d_entries();
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
   }
 
-// widest global access a cell allows: 256-bit (one 32-byte sector per 4-variable fp64 cell), else 128-bit, else scalar
-template <typename T, int NV>
-struct Fv2dVec {
-  static constexpr int BYTES = NV * (int)sizeof(T);
-  static constexpr int NARROW = (BYTES % 16 == 0) ? 16 : (int)sizeof(T);
-  static constexpr int WIDE = (BYTES % 32 == 0) ? 32 : NARROW;
-};
-
 #ifndef EXAHYPE_2D_PF
 #define EXAHYPE_2D_PF 2   // register prefetch distance of the row-marching kernel (rows)
 #endif

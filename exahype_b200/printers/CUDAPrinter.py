@@ -8,8 +8,9 @@ stateless finite-volume Rusanov update of ``examples/Batched_stateless.py:25-35`
   the user's own device source with the reference's ``Functions.h`` signatures),
 * an update functor whose two expressions are printed from the declaration's own statements in SymPy's ``str``
   order, i.e. the evaluation order the reference's generated C++ has, and
-* an ``extern "C"`` entry that instantiates the hand-written kernel template ``csrc/fv_patch_kernel.cuh`` for the
-  declared geometry.
+* an ``extern "C"`` entry that instantiates a hand-written kernel template for the declared geometry: row marching
+  (``csrc/fv2d_march_kernel.cuh``) for 2-D patches whose side divides the warp, plane marching
+  (``csrc/fv3d_march_kernel.cuh``) for 3-D patches, thread per cell (``csrc/fv_patch_kernel.cuh``) otherwise.
 
 ``.code`` / ``.file()`` / ``.here()`` / ``.loop()`` follow ``CodePrinter`` (reference ``CodePrinter.py:46-71``);
 ``.build()`` compiles the unit with nvcc and returns a callable bound through ctypes.
@@ -330,11 +331,12 @@ class CUDAPrinter(CodePrinter):
     dissipation  None: as the reference's printer would emit it (variable 0 only for the reference declaration,
                  CPPPrinter.py:118-126); 'all' / 'var0' to force.
     model        'euler' | 'swe': use a committed hand-written functor family for functions declared without a body.
+    template     'auto' | 'march' | 'cell': which hand-written kernel template the entry instantiates (see module doc).
     """
 
     def __init__(self, kernel: KernelBuilder, function_name: str = "time_step", dtype: str = "f64",
                  dissipation: Optional[str] = None, model: Optional[str] = None,
-                 patches_per_tile: Optional[int] = None, threads: Optional[int] = None):
+                 patches_per_tile: Optional[int] = None, threads: Optional[int] = None, template: str = "auto"):
         super().__init__(kernel, function_name=function_name)
         if dtype not in ("f64", "f32"):
             raise ValueError("dtype must be 'f64' or 'f32'")
@@ -348,6 +350,12 @@ class CUDAPrinter(CodePrinter):
         self.dissipation_all = self.program.dissipation_all if dissipation is None else dissipation == "all"
         self.model = model
         k = kernel
+        if template not in ("auto", "march", "cell"):
+            raise ValueError("template must be 'auto', 'march' or 'cell'")
+        can_march = (k.dim == 2 and k.patch_size in (8, 16, 32)) or (k.dim == 3 and k.patch_size in (4, 8))
+        if template == "march" and not can_march:
+            raise UnsupportedKernel("the marching templates serve 2-D patches of side 8/16/32 and 3-D patches of side 4/8")
+        self.template = "march" if (can_march and (template == "march" or (template == "auto" and k.n_real + k.n_aux <= 6))) else "cell"
         elem = 8 if dtype == "f64" else 4
         G, nt, minb = pick_geometry(k.dim, k.patch_size, k.halo_size, k.n_real, k.n_aux, elem)
         self.patches_per_tile = patches_per_tile or G
@@ -449,8 +457,20 @@ class CUDAPrinter(CodePrinter):
             self.loop([lhs, rhs], d, k.dim + 1, s)
         T = self.ctype
         fname = self.functionName()
-        cfg = lambda da, uh: (f"::exahype::FvKernelConfig<Physics, Update, {T}, {k.dim}, {k.patch_size}, {k.halo_size}, "
-                              f"{self.patches_per_tile}, {self.threads}, {self.min_ctas}, {str(da).lower()}, {str(uh).lower()}>")
+        b = lambda x: str(bool(x)).lower()
+        if self.template == "cell":
+            header = "fv_patch_kernel.cuh"
+            launcher = lambda da, uh: (f"::exahype::FvLauncher<::exahype::FvKernelConfig<Physics, Update, {T}, {k.dim}, "
+                                       f"{k.patch_size}, {k.halo_size}, {self.patches_per_tile}, {self.threads}, "
+                                       f"{self.min_ctas}, {b(da)}, {b(uh)}>>")
+        elif k.dim == 2:
+            header = "fv2d_march_kernel.cuh"
+            launcher = lambda da, uh: (f"::exahype::Fv2dMarchAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
+                                       f"{b(da)}, {b(uh)}>")
+        else:
+            header = "fv3d_march_kernel.cuh"
+            launcher = lambda da, uh: (f"::exahype::Fv3dMarchAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
+                                       f"{b(da)}, {b(uh)}>")
         da = self.dissipation_all
         parts = []
         if self.header_file_name:
@@ -458,10 +478,10 @@ class CUDAPrinter(CodePrinter):
         parts.append(
             "// Generated by exahype.printers.CUDAPrinter -- do not edit.\n"
             f"// Kernel: dim={k.dim} patch_size={k.patch_size} halo_size={k.halo_size} n_real={k.n_real} n_aux={k.n_aux}; "
-            f"dtype={self.dtype}; dissipation={'all' if da else 'var0'}\n"
+            f"dtype={self.dtype}; dissipation={'all' if da else 'var0'}; kernel template: {header}\n"
             "// Statement list (KernelBuilder) and where each statement went in the fused kernel:\n"
             + "".join(self._statements) +
-            "#include <stdint.h>\n#include <cuda_runtime.h>\n#include \"fv_patch_kernel.cuh\"\n\nnamespace {\n\n")
+            f"#include <stdint.h>\n#include <cuda_runtime.h>\n#include \"{header}\"\n\nnamespace {{\n\n")
         parts.append(self._physics())
         parts.append(
             "\n// update statements in the evaluation order of the declaration (SymPy str order == reference C++ order)\n"
@@ -483,8 +503,8 @@ class CUDAPrinter(CodePrinter):
             "  if (n_patches <= 0) return n_patches < 0 ? -1 : 0;\n"
             "  if (!q_in || !q_out || ((uintptr_t)q_in & 15) || ((uintptr_t)q_out & 15)) return -1;\n"
             "  cudaError_t err = (flags & 2u)\n"
-            f"      ? ::exahype::FvLauncher<{cfg(da, True)}>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s)\n"
-            f"      : ::exahype::FvLauncher<{cfg(da, False)}>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);\n"
+            f"      ? {launcher(da, True)}::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s)\n"
+            f"      : {launcher(da, False)}::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);\n"
             "  return err == cudaSuccess ? 0 : -3;\n}\n")
         return "".join(parts)
 

@@ -70,7 +70,13 @@ def test_cuda_printer_recognises_the_program():
     p = CUDAPrinter(k, model="euler")
     assert "using Physics = ::exahype::EulerPhysics<3, 5, 0>;" in p.code
     assert 'extern "C"' in p.code and "int time_step(const void* q_in" in p.code
-    assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true>" in p.code
+    assert '#include "fv3d_march_kernel.cuh"' in p.code
+    assert "::exahype::Fv3dMarchAuto<Physics, Update, double, 8, 1, false, true>::launch" in p.code
+    cell = CUDAPrinter(k, model="euler", template="cell")
+    assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true>" in cell.code
+    assert "Fv2dMarchAuto<Physics, Update, double, 16, 1, false, false>" in CUDAPrinter(
+        batched_stateless(KernelBuilder, 2, 16, 1, 4, 0), model="euler").code
+    assert "FvKernelConfig" in CUDAPrinter(batched_stateless(KernelBuilder, 2, 3, 1, 4, 0), model="euler").code
     assert CUDAPrinter(k, function_name="step32", dtype="f32", dissipation="all", model="euler").code.count("float") >= 2
 
 
