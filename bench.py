@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="patches per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--output", default="unhaloed", choices=["unhaloed", "haloed"])
     ap.add_argument("--dissipation", default="var0", choices=["var0", "all"])
+    ap.add_argument("--reducer", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: all-reduce(max) of lambda over NVLink peer memory (one-shot kernel) or through NCCL")
     ap.add_argument("--kernel", default="auto", choices=["auto", "cell"], help="3-D: plane-marching (auto) or thread-per-cell")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -221,7 +223,7 @@ def main():
     q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
     lam_patch = torch.empty(batch, dtype=tdt, device="cuda")
     lam_max = torch.zeros(1, dtype=tdt, device="cuda")
-    reducer = TimestepReducer(world, rank) if world > 1 else None
+    reducer = TimestepReducer(world, rank, backend=args.reducer) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def step():
@@ -238,6 +240,15 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if reducer is not None:
+        # the collective is exact: the reduced scalar must equal torch.distributed's own MAX over the ranks' local values
+        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+        local = lam_max.clone()
+        reducer.allreduce_max(lam_max)
+        dist.all_reduce(local, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        if float(local.item()) != float(lam_max.item()) or reducer.timed_out():
+            raise SystemExit(f"rank {rank}: all-reduce(max) mismatch: {float(lam_max.item())} vs {float(local.item())}")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -312,7 +323,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": desc, "patches_per_gpu": batch, "global_patches": batch * world,
                        "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)", "kernel_variant": args.kernel,
-                       "parallelism": f"patch-sharded x{world}" + (", NCCL allreduce-max of lambda per step" if world > 1 else ""),
+                       "parallelism": f"patch-sharded x{world}" + (f", allreduce-max of lambda per step ({'one-shot NVLink peer-memory kernel' if reducer.backend == 'peer' else 'NCCL'})" if world > 1 else ""),
                        "l2": "inputs larger than L2: %.2f GB read + %.2f GB written per step per GPU"
                              % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
                        "kernel": info},

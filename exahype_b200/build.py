@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexahype_cuda.so")
 
-SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "synthetic.cu"]
+SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "synthetic.cu", "peer_reduce.cu"]
 HEADERS = ["fv_patch_kernel.cuh", "fv3d_march_kernel.cuh", "fv2d_march_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-lineinfo",
@@ -77,7 +77,7 @@ def _build(force: bool, verbose: bool, extra_flags) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         return r.stderr
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(5, max(1, len(jobs)))) as pool:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as pool:
         for log in pool.map(compile_one, jobs):
             if verbose and log:
                 print(log)

@@ -20,6 +20,13 @@
 #include "fv_registry.h"
 
 namespace exahype {
+struct PeerReducer;   // peer_reduce.cu
+cudaError_t peer_reducer_create(PeerReducer** out, int world, int rank);
+cudaError_t peer_reducer_local_handle(PeerReducer* r, void* out64);
+cudaError_t peer_reducer_connect(PeerReducer* r, const void* all_handles);
+cudaError_t peer_reducer_allreduce_max(PeerReducer* r, void* value, int dtype, cudaStream_t stream);
+cudaError_t peer_reducer_error(PeerReducer* r, int* flag);
+void peer_reducer_destroy(PeerReducer* r);
 cudaError_t fill_synthetic(const exahype_fv_config* cfg, void* q, long long first_cell, long long n_cells,
                            unsigned long long seed, cudaStream_t stream);   // synthetic.cu
 }
@@ -413,6 +420,54 @@ int exahype_cuda_allreduce_max(void* comm, void* values, int64_t count, int dtyp
   int rc = nccl().AllReduce(values, values, (size_t)count, dtype == EXAHYPE_DTYPE_F64 ? ncclFloat64_ : ncclFloat32_,
                             ncclMax_, static_cast<ncclComm_t>(comm), static_cast<cudaStream_t>(stream));
   if (rc != ncclSuccess_) return nccl_fail(rc, "ncclAllReduce(max)");
+  return EXAHYPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot all-reduce(max) over NVLink peer memory (peer_reduce.cu)
+int exahype_cuda_peer_reducer_create(void** reducer, int world_size, int rank) {
+  if (!reducer || world_size < 1 || world_size > 1024 || rank < 0 || rank >= world_size)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "bad reducer arguments (world_size=%d rank=%d)", world_size, rank);
+  exahype::PeerReducer* r = nullptr;
+  cudaError_t err = exahype::peer_reducer_create(&r, world_size, rank);
+  if (err != cudaSuccess) return cuda_fail(err, "peer_reducer_create");
+  *reducer = r;
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_local_handle(void* reducer, void* handle64) {
+  if (!reducer || !handle64) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / handle");
+  cudaError_t err = exahype::peer_reducer_local_handle(static_cast<exahype::PeerReducer*>(reducer), handle64);
+  if (err != cudaSuccess) return cuda_fail(err, "cudaIpcGetMemHandle");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_connect(void* reducer, const void* all_handles) {
+  if (!reducer || !all_handles) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / handles");
+  cudaError_t err = exahype::peer_reducer_connect(static_cast<exahype::PeerReducer*>(reducer), all_handles);
+  if (err != cudaSuccess) return cuda_fail(err, "cudaIpcOpenMemHandle (peer mailbox)");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_allreduce_max(void* reducer, void* value, int dtype, void* stream) {
+  if (!reducer || !value) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / value");
+  if (dtype != EXAHYPE_DTYPE_F64 && dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  cudaError_t err = exahype::peer_reducer_allreduce_max(static_cast<exahype::PeerReducer*>(reducer), value, dtype,
+                                                        static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "peer_allreduce_max_kernel launch");
+  g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_status(void* reducer, int* flag) {
+  if (!reducer || !flag) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / flag");
+  cudaError_t err = exahype::peer_reducer_error(static_cast<exahype::PeerReducer*>(reducer), flag);
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer status");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_destroy(void* reducer) {
+  exahype::peer_reducer_destroy(static_cast<exahype::PeerReducer*>(reducer));
   return EXAHYPE_OK;
 }
 

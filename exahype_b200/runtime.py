@@ -75,6 +75,12 @@ def load(path: Optional[str] = None) -> ctypes.CDLL:
     lib.exahype_cuda_comm_init.argtypes = [ctypes.POINTER(vp), vp, i32, i32]
     lib.exahype_cuda_comm_destroy.argtypes = [vp]
     lib.exahype_cuda_allreduce_max.argtypes = [vp, vp, i64, i32, vp]
+    lib.exahype_cuda_peer_reducer_create.argtypes = [ctypes.POINTER(vp), i32, i32]
+    lib.exahype_cuda_peer_reducer_local_handle.argtypes = [vp, vp]
+    lib.exahype_cuda_peer_reducer_connect.argtypes = [vp, vp]
+    lib.exahype_cuda_peer_reducer_allreduce_max.argtypes = [vp, vp, i32, vp]
+    lib.exahype_cuda_peer_reducer_status.argtypes = [vp, ip]
+    lib.exahype_cuda_peer_reducer_destroy.argtypes = [vp]
     for t, ct in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
         for name in (f"exahype_cuda_fv_step_euler_2d_{t}", f"exahype_cuda_fv_step_euler_3d_{t}",
                      f"exahype_cuda_fv_step_swe_2d_{t}"):

@@ -147,6 +147,24 @@ int exahype_cuda_comm_init(void** comm, const void* id128, int world_size, int r
 int exahype_cuda_comm_destroy(void* comm);
 int exahype_cuda_allreduce_max(void* comm, void* values, int64_t count, int dtype, void* stream);
 
+/*
+ * The same reduction without NCCL: a one-shot all-reduce(max) of ONE scalar over NVLink peer memory (each rank's
+ * mailbox is mapped into every peer through CUDA IPC; one tiny stream-ordered kernel per step stores the local value into
+ * every peer's mailbox and spins on its own).  Latency ~ one NVLink round trip instead of an NCCL launch.  Collective:
+ * every rank calls allreduce_max the same number of times.  One process per GPU, all on one node.
+ *   create        allocates this rank's mailbox on the current device
+ *   local_handle  writes the 64-byte cudaIpcMemHandle_t of the mailbox (the host plumbing all-gathers them)
+ *   connect       maps the world_size * 64 bytes of gathered handles (own entry ignored)
+ *   allreduce_max in place on the device scalar `value` of dtype, asynchronous on stream
+ *   status        *flag = 1 if a wait timed out (a peer never arrived); synchronises the device
+ */
+int exahype_cuda_peer_reducer_create(void** reducer, int world_size, int rank);
+int exahype_cuda_peer_reducer_local_handle(void* reducer, void* handle64);
+int exahype_cuda_peer_reducer_connect(void* reducer, const void* all_handles);
+int exahype_cuda_peer_reducer_allreduce_max(void* reducer, void* value, int dtype, void* stream);
+int exahype_cuda_peer_reducer_status(void* reducer, int* flag);
+int exahype_cuda_peer_reducer_destroy(void* reducer);
+
 #ifdef __cplusplus
 }
 #endif
