@@ -52,13 +52,18 @@ struct Fv2dMarchConfig {
   static constexpr int COMPS = NR + 1 + DV;               // F_1[NR], L_1, Q[DV] cross lanes
   static constexpr int NT = WPC * 32;
   static constexpr int ROW_BYTES = S * CELL_BYTES;        // one haloed row of a patch (contiguous in the AoS batch)
-  // rows are pulled into L2 ahead of the register loads by bulk prefetches (one lane per patch, no registers): the whole
-  // patch at once when it is small, else a window of ~12 KB rolling ahead of the march
+  // rows are pulled into L2 ahead of the register loads by bulk prefetches (one lane per patch, no registers).  The
+  // window is short on purpose: at 6 TB/s some 80 MB stream through the 126 MB L2 every 13 us, so rows requested a
+  // whole patch ahead are evicted again before the march reaches them (measured: +11 % DRAM reads on 32x32 patches).
 #ifndef EXAHYPE_2D_L2
 #define EXAHYPE_2D_L2 1
 #endif
+#ifndef EXAHYPE_2D_L2_BYTES
+#define EXAHYPE_2D_L2_BYTES 2048
+#endif
   static constexpr bool L2_BULK = EXAHYPE_2D_L2 && (ROW_BYTES % 16 == 0);
-  static constexpr int L2_ROWS = (NROW * ROW_BYTES <= 16 * 1024) ? NROW : ((12 * 1024) / ROW_BYTES < 4 ? 4 : (12 * 1024) / ROW_BYTES);
+  static constexpr int L2_ROWS_WANTED = PF + 1 + (EXAHYPE_2D_L2_BYTES + ROW_BYTES - 1) / ROW_BYTES;
+  static constexpr int L2_ROWS = L2_ROWS_WANTED < NROW ? L2_ROWS_WANTED : NROW;
   static_assert(VEC == 32 || VEC == 16 || VEC == (int)sizeof(T), "vector width of the global accesses");
   static_assert(VEC == (int)sizeof(T) || CELL_BYTES % VEC == 0, "a cell must be a whole number of vectors");
 

@@ -75,29 +75,26 @@ FvEntryList swe2d_entries();
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
   }
 
-#ifndef EXAHYPE_2D_PF
-#define EXAHYPE_2D_PF 2   // register prefetch distance of the row-marching kernel (rows)
-#endif
-#define EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WHICH)                                            \
+#define EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, WHICH)                                           \
   ::exahype::Fv2dMarchConfig<PHYS, ::exahype::RusanovUpdate, T, P, H, WPC, MINB, DA, UH,                       \
-                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH, EXAHYPE_2D_PF>
-#define EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, DA, UH)                                              \
-  ::exahype::Fv2dMarchDispatch<EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, WIDE),                     \
-                               EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, DA, UH, NARROW)>
+                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH, PF>
+#define EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, DA, UH)                                             \
+  ::exahype::Fv2dMarchDispatch<EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, WIDE),                     \
+                               EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, NARROW)>
 
-// 2-D shape served by the row-marching kernel (WPC warps per CTA), with the thread-per-cell kernel (G, NT, MINB_CELL) as
+// 2-D shape served by the row-marching kernel (WPC warps per CTA, register prefetch distance PF rows), with the thread-per-cell kernel (G, NT, MINB_CELL) as
 // alternative
-#define EXAHYPE_FV2D_ENTRY(MODEL, DTYPE, PHYS, T, P, H, WPC, MINB, G, NT, MINB_CELL)                             \
+#define EXAHYPE_FV2D_ENTRY(MODEL, DTYPE, PHYS, T, P, H, WPC, MINB, PF, G, NT, MINB_CELL)                            \
   {                                                                                                       \
     {MODEL, DTYPE, 2, P, H, PHYS::NR, PHYS::NA, 0u},                                                      \
-        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, false)::launch,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, false)::launch,                               \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, true)::launch,                               \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, true)::launch},                               \
-        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, false)::prepare,                             \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, false)::prepare,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, false, true)::prepare,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, true, true)::prepare},                              \
+        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, false)::launch,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, false)::launch,                               \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, true)::launch,                               \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, true)::launch},                               \
+        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, false)::prepare,                             \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, false)::prepare,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, true)::prepare,                              \
+         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, true)::prepare},                              \
         {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, false)>::launch,   \
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, false)>::launch,    \
          &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, true)>::launch,    \

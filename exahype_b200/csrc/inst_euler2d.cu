@@ -11,13 +11,13 @@ using E2 = EulerPhysics<2, 4, 0>;
 using E2ref = EulerPhysics<2, 5, 5>;
 
 const FvEntry kEntries[] = {
-    // row-marching kernel (default): WPC warps per CTA, MINB | thread-per-cell kernel: G, NT, MINB
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 16, 1, 4, 4, 1, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E2, float, 16, 1, 4, 4, 1, 256, 2),
+    // row-marching kernel (default): WPC warps per CTA, MINB, PF rows of register prefetch | thread-per-cell kernel: G, NT, MINB
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 16, 1, 4, 4, 2, 1, 256, 2),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E2, float, 16, 1, 4, 4, 3, 1, 256, 2),
     EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 2, 3, 1, 28, 256, 2),
     EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E2, float, 2, 3, 1, 28, 256, 2),
     EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 2, 4, 1, 16, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 8, 1, 4, 4, 4, 256, 2),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 8, 1, 4, 4, 2, 4, 256, 2),
     EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2ref, double, 2, 4, 1, 8, 128, 2),
 };
 }  // namespace

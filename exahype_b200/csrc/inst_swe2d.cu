@@ -8,11 +8,11 @@ namespace {
 using SW = SwePhysics<3, 1>;
 
 const FvEntry kEntries[] = {
-    // row-marching kernel (default): WPC warps per CTA, MINB | thread-per-cell kernel: G, NT, MINB
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 32, 1, 4, 4, 1, 512, 1),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 32, 1, 4, 4, 1, 512, 1),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 16, 1, 4, 4, 1, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 16, 1, 4, 4, 1, 256, 2),
+    // row-marching kernel (default): WPC warps per CTA, MINB, PF rows of register prefetch | thread-per-cell kernel: G, NT, MINB
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 32, 1, 4, 4, 3, 1, 512, 1),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 32, 1, 4, 4, 3, 1, 512, 1),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 16, 1, 4, 4, 2, 1, 256, 2),
+    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 16, 1, 4, 4, 3, 1, 256, 2),
 };
 }  // namespace
 
