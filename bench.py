@@ -388,6 +388,33 @@ def time_variants(torch, runtime, args):
                 res[f"{wl}/{output}/{diss}" + ("/cell-kernel" if kern == "cell" else "")] = {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
                                                 "algorithmic_GBs": gbs}
                 del q_in, q_out
+    # the CellData form (per-patch pointers + per-patch dt) on the headline workload: same kernel, gathered addressing
+    for wl in ("c3", "c2"):
+        model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
+        tdt = torch.float64
+        upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, output="unhaloed")
+        q_in = synthetic_on_device(torch, upd, 0, batch, tdt)
+        q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
+        perm = torch.randperm(batch, device="cuda")
+        per_in, per_out = q_in[0].numel() * 8, q_out[0].numel() * 8
+        in_ptrs = q_in.data_ptr() + perm * per_in
+        out_ptrs = q_out.data_ptr() + perm * per_out
+        dts = torch.full((batch,), 0.01, dtype=tdt, device="cuda")
+        lam = torch.zeros(1, dtype=tdt, device="cuda")
+        for _ in range(3):
+            upd.step_cell_data(in_ptrs, out_ptrs, dt_patch=dts, lambda_max=lam)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            upd.step_cell_data(in_ptrs, out_ptrs, dt_patch=dts, lambda_max=lam)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        res[f"{wl}/unhaloed/var0/cell-data (permuted patch pointers, per-patch dt)"] = {
+            "ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
+            "algorithmic_GBs": upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9}
+        del q_in, q_out
     return res
 
 

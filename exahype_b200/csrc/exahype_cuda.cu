@@ -190,8 +190,30 @@ int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
   const int var = variant_of(cfg->flags);
   const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
-  cudaError_t err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);
+  cudaError_t err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, nullptr);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch");
+  g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_cell_data* cells, double dt,
+                                   void* lambda_max, void* stream) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  if (!cells) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cells is null");
+  if (cells->n_patches < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_patches must be >= 0 (got %lld)", (long long)cells->n_patches);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (lambda_max && !(cfg->flags & EXAHYPE_FLAG_LAMBDA_ACCUMULATE)) {
+    cudaError_t err = cudaMemsetAsync(lambda_max, 0, elem_size(cfg->dtype), s);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaMemsetAsync(lambda_max)");
+  }
+  if (cells->n_patches == 0) return EXAHYPE_OK;
+  if (!cells->q_in || !cells->q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cells->q_in / cells->q_out must not be null");
+  const exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt};
+  const int var = variant_of(cfg->flags);   // the CellData form exists for the shape's default kernel
+  cudaError_t err = e->gather_launch[var](nullptr, nullptr, cells->n_patches, dt, cells->max_eigenvalue, lambda_max, s, &g);
+  if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (cell data)");
   g_launches.fetch_add(1);
   return EXAHYPE_OK;
 }

@@ -28,7 +28,7 @@
 namespace exahype {
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int WPC_, int MINB_, bool DISS_ALL_, bool UNHALOED_,
-          int VEC_, int PF_ = 2>
+          int VEC_, int PF_ = 2, bool GATHER_ = false>
 struct Fv2dMarchConfig {
   using Phys = Phys_;
   using Upd = Upd_;
@@ -37,7 +37,7 @@ struct Fv2dMarchConfig {
   static constexpr int PF = PF_;                          // rows between a register load and its use
   static constexpr int RING = PF + 2;                     // rows r-1, r, r+1 .. r+PF live in registers
   static_assert(PF >= 1 && PF <= 4, "register prefetch distance");
-  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_;
+  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_, GATHER = GATHER_;
   static_assert(P >= 1 && P <= 32 && 32 % P == 0, "row marching needs a patch side that divides the warp");
   static_assert(H >= 1 && WPC >= 1 && WPC <= 32, "march geometry");
 
@@ -252,7 +252,8 @@ __device__ __forceinline__ bool march_ring(const RowMarch<C>& m, int& r, A&... a
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
-                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max) {
+                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max,
+                  const FvGather<typename C::T> gather) {
   using T = typename C::T;
   using Phys = typename C::Phys;
   using Bits = typename FloatBits<T>::type;
@@ -266,7 +267,6 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
 
   RowMarch<C> m;
   m.X = reinterpret_cast<T*>(smem + warp * C::WARP_BYTES);
-  m.dt = dt;
   m.lane = lane;
   const int sub = lane / P;
   m.k = lane - sub * P;
@@ -276,10 +276,13 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   long long patch = first_patch + sub;
   m.store_ok = patch < n_patches;
   if (!m.store_ok) patch = n_patches - 1;
-  m.row_ptr = q_in + patch * (long long)C::PATCH_ELEMS + ((long long)(H - 1) * S + (m.k + H)) * NV;
-  m.out_ptr = C::UNHALOED ? q_out + patch * (long long)C::OUT_PATCH_ELEMS + m.k * NV
-                          : q_out + patch * (long long)C::PATCH_ELEMS + ((long long)H * S + (m.k + H)) * NV;
-  m.l2_ptr = reinterpret_cast<const unsigned char*>(q_in + patch * (long long)C::PATCH_ELEMS + (long long)(H - 1) * S * NV);
+  // CellData form: this lane's patch through its own pointers, with its own time step
+  const T* const patch_in = gather.template in<C::GATHER>(q_in, patch, C::PATCH_ELEMS);
+  m.dt = gather.template step<C::GATHER>(dt, patch);
+  m.row_ptr = patch_in + ((long long)(H - 1) * S + (m.k + H)) * NV;
+  m.out_ptr = C::UNHALOED ? gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + m.k * NV
+                          : gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + ((long long)H * S + (m.k + H)) * NV;
+  m.l2_ptr = reinterpret_cast<const unsigned char*>(patch_in + (long long)(H - 1) * S * NV);
   if (C::L2_BULK && m.k == 0) l2_prefetch_bulk(m.l2_ptr, C::L2_ROWS * C::ROW_BYTES);
 
   T q[C::RING][NV], f0[C::RING][NR], l0[C::RING], l1_mid = T(0), q_old[DV], lam_local = T(0);
@@ -300,9 +303,7 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
 
   {
     // ------------------------------------------------------------------ face-halo table: lane <-> (patch, interior row)
-    long long hp = first_patch + sub;
-    if (hp >= n_patches) hp = n_patches - 1;
-    const T* left = q_in + hp * (long long)C::PATCH_ELEMS + ((long long)(m.k + H) * S + (H - 1)) * NV;   // row = m.k
+    const T* left = patch_in + ((long long)(m.k + H) * S + (H - 1)) * NV;   // row = m.k of this lane's own patch
     T ql[NV], qr[NV];
     load_cell<C>(left, ql);
     load_cell<C>(left + (P + 1) * NV, qr);
@@ -365,7 +366,7 @@ struct Fv2dMarchLauncher {
   }
 
   static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
-                            void* lambda_max, cudaStream_t stream) {
+                            void* lambda_max, cudaStream_t stream, const FvGatherRaw* gather = nullptr) {
     using T = typename C::T;
     if (n_patches <= 0) return cudaSuccess;
     FvLaunchInfo info;
@@ -373,7 +374,7 @@ struct Fv2dMarchLauncher {
     if (err != cudaSuccess) return err;
     fv2d_march_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
         static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
-        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max));
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), make_gather<T>(gather));
     return cudaGetLastError();
   }
 };
@@ -388,9 +389,9 @@ struct Fv2dMarchDispatch {
     return Fv2dMarchLauncher<C32>::prepare(info, n_patches);
   }
   static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
-                            void* lambda_max, cudaStream_t stream) {
-    if (wide(q_in, q_out)) return Fv2dMarchLauncher<C32>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
-    return Fv2dMarchLauncher<C16>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
+                            void* lambda_max, cudaStream_t stream, const FvGatherRaw* gather = nullptr) {
+    if (wide(q_in, q_out)) return Fv2dMarchLauncher<C32>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream, gather);
+    return Fv2dMarchLauncher<C16>::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream, gather);
   }
 };
 
@@ -399,5 +400,9 @@ template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 using Fv2dMarchAuto =
     Fv2dMarchDispatch<Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::WIDE>,
                       Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW>>;
+// CellData form: gathered patches are only known to be 16-byte aligned individually -> narrow accesses
+template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH, int PF = 2>
+using Fv2dMarchGather =
+    Fv2dMarchLauncher<Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW, PF, true>>;
 
 }  // namespace exahype

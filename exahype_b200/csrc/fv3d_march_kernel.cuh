@@ -27,13 +27,13 @@
 namespace exahype {
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int NG_, int R_, int MINB_, bool DISS_ALL_,
-          bool UNHALOED_>
+          bool UNHALOED_, bool GATHER_ = false>
 struct Fv3dMarchConfig {
   using Phys = Phys_;
   using Upd = Upd_;
   using T = T_;
   static constexpr int DIM = 3, P = P_, H = H_, NG = NG_, R = R_, MINB = MINB_;
-  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_;
+  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_, GATHER = GATHER_;
   static_assert(P >= 1 && H >= 1 && NG >= 1 && NG <= 15 && R >= 3, "march geometry");
 
   static constexpr int NR = Phys::NR, NA = Phys::NA, NV = NR + NA;
@@ -125,11 +125,13 @@ struct MarchStream {
   // producer cursor (thread 0 of the group): next plane to request
   int p_seq, p_ip, p_pi, p_slot;
 
-  __device__ __forceinline__ void issue_next_load() {
+  // `gather` (CellData form: per-patch pointers / time steps, used by GATHER instantiations only) is always the kernel
+  // parameter itself, read from the constant bank where it is used instead of occupying registers
+  __device__ __forceinline__ void issue_next_load(const FvGather<T>& gather) {
     const long long patch = g_index + (long long)p_pi * n_groups;
     mbar_expect_tx(&full[p_slot], C::PLANE_BYTES);
     tma_load_1d(ring + p_slot * C::PLANE_ELEMS,
-                q_in + patch * (long long)C::PATCH_ELEMS + (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS,
+                gather.template in<C::GATHER>(q_in, patch, C::PATCH_ELEMS) + (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS,
                 C::PLANE_BYTES, &full[p_slot]);
     ++p_seq;
     if (++p_ip == C::NPL) { p_ip = 0; ++p_pi; }
@@ -148,11 +150,11 @@ struct MarchStream {
 
   // After the group barrier of an iteration: write out the plane updated (staged) in it -- zero-based interior plane
   // `plane` of patch pi, sitting in staging buffer `buffer`.  Executed by the interior warps; thread 0 issues the TMA stores.
-  __device__ __forceinline__ void drain_staged_plane(int plane, int buffer, int n_drain_threads) {
+  __device__ __forceinline__ void drain_staged_plane(const FvGather<T>& gather, int plane, int buffer, int n_drain_threads) {
     const long long patch = g_index + (long long)pi * n_groups;
     const T* sbuf = stage + buffer * (C::STAGE_SEGS * C::SEG_PITCH);
     if (C::UNHALOED) {
-      T* dst = q_out + patch * (long long)C::OUT_PATCH_ELEMS + (long long)plane * C::OUT_PLANE_ELEMS;
+      T* dst = gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + (long long)plane * C::OUT_PLANE_ELEMS;
       if (C::USE_TMA_STORE) {
         if (gt == 0) {
 #pragma unroll
@@ -168,7 +170,7 @@ struct MarchStream {
       }
     } else {
       // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
-      T* dst = q_out + patch * (long long)C::PATCH_ELEMS + (long long)(plane + C::H) * C::PLANE_ELEMS;
+      T* dst = gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + (long long)(plane + C::H) * C::PLANE_ELEMS;
       constexpr int ROW = C::P * C::NV;
       for (int e = gt; e < C::OUT_PLANE_ELEMS; e += n_drain_threads) {
         const int row = e / ROW;
@@ -193,7 +195,8 @@ struct MarchStream {
 enum { MARCH_FIRST = 0, MARCH_SECOND = 1, MARCH_MIDDLE = 2, MARCH_LAST = 3 };
 
 template <class C, int PH, int KIND>
-__device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int ip, int cell, int sj, int sk, int st,
+__device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, const FvGather<typename C::T>& gather, int ip,
+                                                    int cell, int sj, int sk, int st,
                                                     typename C::T (&q)[3][C::NV], typename C::T (&fi)[3][C::NR],
                                                     typename C::T (&li)[3], typename C::T (&lj)[3],
                                                     typename C::T (&lk)[3], typename C::T& lam_local,
@@ -287,10 +290,10 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int ip, 
   named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
 
   // ------------------------------------------------------------ drain, prefetch, publish
-  if constexpr (UPDATE) ms.drain_staged_plane(ip - 2, wb, C::FACE_BASE);
+  if constexpr (UPDATE) ms.drain_staged_plane(gather, ip - 2, wb, C::FACE_BASE);
   if (ms.gt == 0) {
     // the previous plane of the stream was last read by the update above: its ring slot takes the next plane to request
-    if ((KIND != MARCH_FIRST || ms.pi >= 1) && ms.p_seq < ms.n_seq) ms.issue_next_load();
+    if ((KIND != MARCH_FIRST || ms.pi >= 1) && ms.p_seq < ms.n_seq) ms.issue_next_load(gather);
     if constexpr (LAST) {
       const Bits b = ms.lam_slot[ms.pi & 1];
       ms.lam_slot[ms.pi & 1] = 0;                           // next used two patches from now
@@ -303,21 +306,23 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, int ip, 
 
 // all planes of one patch for an interior column: first, second, middle planes 2..P (three phases in rotation), last
 template <class C, class... A>
-__device__ __forceinline__ void march_interior_patch(MarchStream<C>& ms, A&... a) {
-  march_interior_step<C, 0, MARCH_FIRST>(ms, 0, a...);
-  march_interior_step<C, 1, MARCH_SECOND>(ms, 1, a...);
+__device__ __forceinline__ void march_interior_patch(MarchStream<C>& ms, const FvGather<typename C::T>& gather, A&... a) {
+  if constexpr (C::GATHER)   // CellData::dt of this patch
+    if (gather.dt != nullptr) ms.dt = gather.dt[ms.g_index + (long long)ms.pi * ms.n_groups];
+  march_interior_step<C, 0, MARCH_FIRST>(ms, gather, 0, a...);
+  march_interior_step<C, 1, MARCH_SECOND>(ms, gather, 1, a...);
   if constexpr (C::P >= 2) {
     int ip = 2;
     while (true) {
-      march_interior_step<C, 2, MARCH_MIDDLE>(ms, ip, a...);
+      march_interior_step<C, 2, MARCH_MIDDLE>(ms, gather, ip, a...);
       if (++ip > C::P) break;
-      march_interior_step<C, 0, MARCH_MIDDLE>(ms, ip, a...);
+      march_interior_step<C, 0, MARCH_MIDDLE>(ms, gather, ip, a...);
       if (++ip > C::P) break;
-      march_interior_step<C, 1, MARCH_MIDDLE>(ms, ip, a...);
+      march_interior_step<C, 1, MARCH_MIDDLE>(ms, gather, ip, a...);
       if (++ip > C::P) break;
     }
   }
-  march_interior_step<C, (C::P + 1) % 3, MARCH_LAST>(ms, C::P + 1, a...);
+  march_interior_step<C, (C::P + 1) % 3, MARCH_LAST>(ms, gather, C::P + 1, a...);
 }
 
 // One plane for a face-halo column of axis AXIS (1 or 2): F_AXIS and L_AXIS of the cell one layer outside the interior.
@@ -343,7 +348,8 @@ __device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const 
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
-                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max) {
+                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max,
+                  const FvGather<typename C::T> gather) {
   using T = typename C::T;
   using Bits = typename FloatBits<T>::type;
   constexpr int P = C::P, H = C::H, S = C::S, NV = C::NV, NR = C::NR, R = C::R, NPL = C::NPL;
@@ -383,7 +389,7 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   ms.parity = 0;
   ms.p_seq = ms.p_ip = ms.p_pi = ms.p_slot = 0;
   if (gt == 0)
-    for (int s = 0; s < R && ms.p_seq < ms.n_seq; ++s) ms.issue_next_load();
+    for (int s = 0; s < R && ms.p_seq < ms.n_seq; ++s) ms.issue_next_load(gather);
 
   if (gt < C::FACE_BASE) {
     // ======================================================== interior columns (whole warps; lanes past N_INT idle along)
@@ -408,7 +414,7 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     // lanes past N_INT (patch sizes whose P*P is not a multiple of 32) recompute column (0,0) and write the same
     // values to the same places as lane 0: harmless, and it keeps every warp whole for the shuffles and barriers
     for (; ms.pi < ms.n_my_patches; ++ms.pi)
-      march_interior_patch<C>(ms, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
+      march_interior_patch<C>(ms, gather, cell, sj, sk, st, q, fi, li, lj, lk, lam_local, group_lam);
     if (gt == 0) {
       if (C::USE_TMA_STORE) tma_store_wait_all();
       if (lambda_max != nullptr && group_lam != 0) atomicMax(reinterpret_cast<Bits*>(lambda_max), group_lam);
@@ -473,7 +479,7 @@ struct Fv3dMarchLauncher {
   }
 
   static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
-                            void* lambda_max, cudaStream_t stream) {
+                            void* lambda_max, cudaStream_t stream, const FvGatherRaw* gather = nullptr) {
     using T = typename C::T;
     if (n_patches <= 0) return cudaSuccess;
     FvLaunchInfo info;
@@ -481,7 +487,7 @@ struct Fv3dMarchLauncher {
     if (err != cudaSuccess) return err;
     fv3d_march_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
         static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
-        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max));
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), make_gather<T>(gather));
     return cudaGetLastError();
   }
 };
@@ -496,6 +502,7 @@ struct Fv3dMarchAutoConfig {
   static constexpr int NG0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int NG = NG0 < 1 ? 1 : (NG0 > 15 ? 15 : NG0);
   using type = Fv3dMarchConfig<Phys, Upd, T, P, H, NG, 5, 1, DA, UH>;
+  using gather_type = Fv3dMarchConfig<Phys, Upd, T, P, H, NG, 5, 1, DA, UH, true>;
 };
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 using Fv3dMarchAuto = Fv3dMarchLauncher<typename Fv3dMarchAutoConfig<Phys, Upd, T, P, H, DA, UH>::type>;

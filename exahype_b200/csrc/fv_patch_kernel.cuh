@@ -46,16 +46,57 @@ template <> struct FloatBits<float> {
   static __device__ __forceinline__ float from(type b) { return __uint_as_float(b); }
 };
 
+// ExaHyPE2 CellData form of a batch (reference examples/kernel-generator.py:8-19, the QIn / QOut / dt members of
+// `::exahype2::CellData&`): patch p lives at q_in[p] / q_out[p] instead of base + p * stride and advances by its own
+// dt[p] (null dt: the scalar).  Kernels are instantiated twice, GATHER = false (dense batch: the struct is dead and
+// costs nothing; a run-time switch measured 3.5 % on the dense path) and GATHER = true.
+template <typename T>
+struct FvGather {
+  const T* const* q_in = nullptr;
+  T* const* q_out = nullptr;
+  const T* dt = nullptr;
+  template <bool GATHER>
+  __device__ __forceinline__ const T* in(const T* base, long long patch, int patch_elems) const {
+    if constexpr (GATHER) return q_in[patch];
+    else return base + patch * (long long)patch_elems;
+  }
+  template <bool GATHER>
+  __device__ __forceinline__ T* out(T* base, long long patch, int patch_elems) const {
+    if constexpr (GATHER) return q_out[patch];
+    else return base + patch * (long long)patch_elems;
+  }
+  template <bool GATHER>
+  __device__ __forceinline__ T step(T scalar, long long patch) const {
+    if constexpr (GATHER) return dt ? dt[patch] : scalar;
+    else return scalar;
+  }
+};
+struct FvGatherRaw {   // type-erased form crossing the registry's function pointers
+  const void* const* q_in;
+  void* const* q_out;
+  const void* dt;
+};
+template <typename T>
+inline FvGather<T> make_gather(const FvGatherRaw* raw) {
+  FvGather<T> g;
+  if (raw) {
+    g.q_in = reinterpret_cast<const T* const*>(raw->q_in);
+    g.q_out = reinterpret_cast<T* const*>(raw->q_out);
+    g.dt = static_cast<const T*>(raw->dt);
+  }
+  return g;
+}
+
 // ------------------------------------------------------------------------------------------------
 // compile-time geometry of one instantiation
 template <class Phys_, class Upd_, typename T_, int DIM_, int P_, int H_, int G_, int NT_, int MINB_,
-          bool DISS_ALL_, bool UNHALOED_>
+          bool DISS_ALL_, bool UNHALOED_, bool GATHER_ = false>
 struct FvKernelConfig {
   using Phys = Phys_;
   using Upd = Upd_;
   using T = T_;
   static constexpr int DIM = DIM_, P = P_, H = H_, G = G_, NT = NT_, MINB = MINB_;
-  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_;
+  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_, GATHER = GATHER_;
   static_assert(DIM == 2 || DIM == 3, "dim");
   static_assert(P >= 1 && H >= 1 && G >= 1, "patch geometry");
   static_assert(NT % 32 == 0 && NT <= 1024, "threads per CTA");
@@ -220,7 +261,8 @@ __device__ __forceinline__ void eval_face(int f, int npatch, const typename C::T
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches,   // q_out may alias q_in
-               typename C::T dt, typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max) {
+               typename C::T dt, typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max,
+               const FvGather<typename C::T> gather) {
   using T = typename C::T;
   using Phys = typename C::Phys;
   using Upd = typename C::Upd;
@@ -248,13 +290,21 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
   if (tid < 2 * G) lam_bits[tid] = 0;
   __syncthreads();
 
-  long long tile = blockIdx.x;
-  if (C::USE_TMA_LOAD && tid == 0 && tile < n_tiles) {
-    const long long np = (n_patches - tile * G < G) ? (n_patches - tile * G) : G;
+  // one bulk copy per tile of a dense batch; one per patch when the patches are gathered through pointers
+  auto request_tile = [&](long long t, int b) {
+    const long long np = (n_patches - t * G < G) ? (n_patches - t * G) : G;
     const uint32_t bytes = (uint32_t)np * C::PATCH_BYTES;
-    mbar_expect_tx(&mbar[0], bytes);
-    tma_load_1d(qbuf, q_in + tile * (long long)C::TILE_ELEMS, bytes, &mbar[0]);
-  }
+    mbar_expect_tx(&mbar[b], bytes);
+    if constexpr (!C::GATHER) {
+      tma_load_1d(qbuf + b * C::TILE_ELEMS, q_in + t * (long long)C::TILE_ELEMS, bytes, &mbar[b]);
+    } else {
+      for (int g = 0; g < (int)np; ++g)
+        tma_load_1d(qbuf + b * C::TILE_ELEMS + g * C::PATCH_ELEMS, gather.q_in[t * G + g], C::PATCH_BYTES, &mbar[b]);
+    }
+  };
+
+  long long tile = blockIdx.x;
+  if (C::USE_TMA_LOAD && tid == 0 && tile < n_tiles) request_tile(tile, 0);
 
   Bits cta_lam = 0;   // running maximum of the patches this thread published (threads < G)
 
@@ -267,17 +317,14 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
     if (C::USE_TMA_LOAD) {
       if (tid == 0) {
         const long long next = tile + gridDim.x;
-        if (next < n_tiles) {   // buffer buf^1 was last read in phase B of the previous tile (barrier passed)
-          const long long np = (n_patches - next * G < G) ? (n_patches - next * G) : G;
-          const uint32_t bytes = (uint32_t)np * C::PATCH_BYTES;
-          mbar_expect_tx(&mbar[buf ^ 1], bytes);
-          tma_load_1d(qbuf + (buf ^ 1) * C::TILE_ELEMS, q_in + next * (long long)C::TILE_ELEMS, bytes, &mbar[buf ^ 1]);
-        }
+        if (next < n_tiles) request_tile(next, buf ^ 1);   // buffer buf^1 was last read in phase B of the previous tile
       }
       mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
     } else {
-      const T* src = q_in + tile * (long long)C::TILE_ELEMS;
-      for (int i = tid; i < npatch * C::PATCH_ELEMS; i += NT) qbuf[i] = src[i];
+      for (int i = tid; i < npatch * C::PATCH_ELEMS; i += NT) {
+        const int g = i / C::PATCH_ELEMS;
+        qbuf[i] = gather.template in<C::GATHER>(q_in, tile * G + g, C::PATCH_ELEMS)[i - g * C::PATCH_ELEMS];
+      }
       __syncthreads();
     }
 
@@ -361,6 +408,7 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
       const int e = tid + r * NT;
       if (e < npatch * C::PD) {
         const CellIndex<C> ci = interior_cell<C>(e);
+        const T dt_cell = gather.template step<C::GATHER>(dt, tile * G + ci.g);
         T qc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) qc[v] = q[r][v];
@@ -395,7 +443,7 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
               q_plus = Qv[dc * NV];
               q_minus = Qv[-dc * NV];
             }
-            qc[v] = Upd::dissipation(qc[v], q[r][v], q_plus, q_minus, lam[r][n], l_plus, l_minus, dt);
+            qc[v] = Upd::dissipation(qc[v], q[r][v], q_plus, q_minus, lam[r][n], l_plus, l_minus, dt_cell);
           }
         }
         T* dst = stage + e * NV;
@@ -408,19 +456,27 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
 
     // ---------------------------------------------------------------- phase C: staged interior -> HBM
     if (C::UNHALOED) {
-      T* dst = q_out + tile * (long long)C::OUT_ELEMS;
       if (C::USE_TMA_STORE) {
         if (tid == 0) {
-          tma_store_1d(dst, stage, (uint32_t)npatch * C::OUT_PATCH_ELEMS * (uint32_t)sizeof(T));
+          if constexpr (!C::GATHER) {
+            tma_store_1d(q_out + tile * (long long)C::OUT_ELEMS, stage,
+                         (uint32_t)npatch * C::OUT_PATCH_ELEMS * (uint32_t)sizeof(T));
+          } else {
+            for (int g = 0; g < npatch; ++g)
+              tma_store_1d(gather.q_out[tile * G + g], stage + g * C::OUT_PATCH_ELEMS,
+                           C::OUT_PATCH_ELEMS * (uint32_t)sizeof(T));
+          }
           tma_store_commit();
         }
       } else {
-        for (int i = tid; i < npatch * C::OUT_PATCH_ELEMS; i += NT) dst[i] = stage[i];
+        for (int i = tid; i < npatch * C::OUT_PATCH_ELEMS; i += NT) {
+          const int g = i / C::OUT_PATCH_ELEMS;
+          gather.template out<C::GATHER>(q_out, tile * G + g, C::OUT_PATCH_ELEMS)[i - g * C::OUT_PATCH_ELEMS] = stage[i];
+        }
       }
     } else {
       // haloed layout: interior rows are contiguous runs of P*NV values (test.cpp:96-104 writes all NV)
       constexpr int ROW = C::P * NV;
-      T* dst = q_out + tile * (long long)C::TILE_ELEMS;
       for (int i = tid; i < npatch * C::OUT_PATCH_ELEMS; i += NT) {
         const int row = i / ROW;          // (patch, x_0 .. x_{DIM-2})
         const int col = i - row * ROW;
@@ -431,7 +487,7 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
           cell += (r % C::P + C::H) * C::cell_stride(m);
           r /= C::P;
         }
-        dst[(r * C::NCELL + cell) * NV + col] = stage[i];
+        gather.template out<C::GATHER>(q_out, tile * G + r, C::PATCH_ELEMS)[cell * NV + col] = stage[i];   // r is now the patch of the tile
       }
     }
   }
@@ -479,7 +535,7 @@ struct FvLauncher {
   }
 
   static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
-                            void* lambda_max, cudaStream_t stream) {
+                            void* lambda_max, cudaStream_t stream, const FvGatherRaw* gather = nullptr) {
     using T = typename C::T;
     if (n_patches <= 0) return cudaSuccess;
     FvLaunchInfo info;
@@ -487,7 +543,7 @@ struct FvLauncher {
     if (err != cudaSuccess) return err;
     fv_step_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
         static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
-        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max));
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), make_gather<T>(gather));
     return cudaGetLastError();
   }
 };

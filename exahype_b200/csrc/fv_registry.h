@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "../../include/exahype_cuda.h"
 #include "fv_patch_kernel.cuh"
 #include "fv3d_march_kernel.cuh"
@@ -10,7 +12,7 @@
 
 namespace exahype {
 
-using FvLaunchFn = cudaError_t (*)(const void*, void*, long long, double, void*, void*, cudaStream_t);
+using FvLaunchFn = cudaError_t (*)(const void*, void*, long long, double, void*, void*, cudaStream_t, const FvGatherRaw*);
 using FvPrepareFn = cudaError_t (*)(FvLaunchInfo*, long long);
 
 struct FvEntry {
@@ -21,6 +23,8 @@ struct FvEntry {
   // selected with EXAHYPE_FLAG_KERNEL_CELL, null when there is only one kernel
   FvLaunchFn alt_launch[4];
   FvPrepareFn alt_prepare[4];
+  // the default kernel instantiated for the CellData form (per-patch pointers / time steps): exahype_cuda_fv_step_cell_data
+  FvLaunchFn gather_launch[4];
 };
 
 struct FvEntryList {
@@ -32,77 +36,72 @@ FvEntryList euler2d_entries();
 FvEntryList euler3d_entries();
 FvEntryList swe2d_entries();
 
-#define EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, DA, UH) \
-  ::exahype::FvKernelConfig<PHYS, ::exahype::RusanovUpdate, T, DIM, P, H, G, NT, MINB, DA, UH>
-
-// one committed shape = four kernels (dissipation var0|all  x  output haloed|un-haloed)
-#define EXAHYPE_FV_ENTRY(MODEL, DTYPE, PHYS, T, DIM, P, H, G, NT, MINB)                                   \
-  {                                                                                                       \
-    {MODEL, DTYPE, DIM, P, H, PHYS::NR, PHYS::NA, 0u},                                                    \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, false)>::launch,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, false)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, true)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, true)>::launch},    \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, false)>::prepare,  \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, false)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, false, true)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, DIM, P, H, G, NT, MINB, true, true)>::prepare},   \
-        {nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}                        \
+// A committed shape is described by up to three launcher families, each a template over (DISSIPATION_ALL, UNHALOED):
+// Main (default kernel, dense batch), Gather (same kernel, CellData form) and Alt (second kernel, or NoKernel).
+template <bool DA, bool UH>
+struct NoKernel {
+  static constexpr bool exists = false;
+  static cudaError_t prepare(FvLaunchInfo*, long long) { return cudaErrorNotSupported; }
+  static cudaError_t launch(const void*, void*, long long, double, void*, void*, cudaStream_t, const FvGatherRaw*) {
+    return cudaErrorNotSupported;
   }
+};
+template <class L, class = void> struct launcher_exists { static constexpr bool value = true; };
+template <class L> struct launcher_exists<L, std::enable_if_t<!L::exists>> { static constexpr bool value = false; };
 
-#define EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, DA, UH) \
-  ::exahype::Fv3dMarchConfig<PHYS, ::exahype::RusanovUpdate, T, P, H, NG, R, MINB, DA, UH>
-
-// 3-D shape served by the plane-marching kernel, with the thread-per-cell kernel (G, NT, MINB_CELL) as alternative
-#define EXAHYPE_FV3D_ENTRY(MODEL, DTYPE, PHYS, T, P, H, NG, R, MINB, G, NT, MINB_CELL)                           \
-  {                                                                                                       \
-    {MODEL, DTYPE, 3, P, H, PHYS::NR, PHYS::NA, 0u},                                                      \
-        {&::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, false, false)>::launch,     \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, true, false)>::launch,      \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, false, true)>::launch,      \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, true, true)>::launch},      \
-        {&::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, false, false)>::prepare,    \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, true, false)>::prepare,     \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, false, true)>::prepare,     \
-         &::exahype::Fv3dMarchLauncher<EXAHYPE_MARCH_CFG(PHYS, T, P, H, NG, R, MINB, true, true)>::prepare},     \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, false, false)>::launch,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, false)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, false, true)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, true)>::launch},    \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, false, false)>::prepare,  \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, false)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, false, true)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 3, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
+template <template <bool, bool> class Main, template <bool, bool> class Gather, template <bool, bool> class Alt>
+inline FvEntry make_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
+  constexpr bool alt = launcher_exists<Alt<false, false>>::value;
+  FvEntry e = {};
+  e.cfg = {model, dtype, dim, P, H, nr, na, 0u};
+  FvLaunchFn ml[4] = {&Main<false, false>::launch, &Main<true, false>::launch, &Main<false, true>::launch, &Main<true, true>::launch};
+  FvPrepareFn mp[4] = {&Main<false, false>::prepare, &Main<true, false>::prepare, &Main<false, true>::prepare, &Main<true, true>::prepare};
+  FvLaunchFn gl[4] = {&Gather<false, false>::launch, &Gather<true, false>::launch, &Gather<false, true>::launch, &Gather<true, true>::launch};
+  FvLaunchFn al[4] = {&Alt<false, false>::launch, &Alt<true, false>::launch, &Alt<false, true>::launch, &Alt<true, true>::launch};
+  FvPrepareFn ap[4] = {&Alt<false, false>::prepare, &Alt<true, false>::prepare, &Alt<false, true>::prepare, &Alt<true, true>::prepare};
+  for (int i = 0; i < 4; ++i) {
+    e.launch[i] = ml[i];
+    e.prepare[i] = mp[i];
+    e.gather_launch[i] = gl[i];
+    e.alt_launch[i] = alt ? al[i] : nullptr;
+    e.alt_prepare[i] = alt ? ap[i] : nullptr;
   }
+  return e;
+}
 
-#define EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, WHICH)                                           \
-  ::exahype::Fv2dMarchConfig<PHYS, ::exahype::RusanovUpdate, T, P, H, WPC, MINB, DA, UH,                       \
-                             ::exahype::Fv2dVec<T, PHYS::NR + PHYS::NA>::WHICH, PF>
-#define EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, DA, UH)                                             \
-  ::exahype::Fv2dMarchDispatch<EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, WIDE),                     \
-                               EXAHYPE_MARCH2D_CFG(PHYS, T, P, H, WPC, MINB, PF, DA, UH, NARROW)>
+// ---- launcher families for the three kernel templates (RusanovUpdate is the update functor of every committed shape)
+// thread per cell: G patches per tile, NT threads, MINB CTAs per SM
+template <class Phys, typename T, int DIM, int P, int H, int G, int NT, int MINB>
+struct CellFamily {
+  template <bool DA, bool UH> using Dense = FvLauncher<FvKernelConfig<Phys, RusanovUpdate, T, DIM, P, H, G, NT, MINB, DA, UH, false>>;
+  template <bool DA, bool UH> using Gather = FvLauncher<FvKernelConfig<Phys, RusanovUpdate, T, DIM, P, H, G, NT, MINB, DA, UH, true>>;
+};
+// 3-D plane marching: NG groups per CTA, ring of R planes, MINB CTAs per SM
+template <class Phys, typename T, int P, int H, int NG, int R, int MINB>
+struct March3dFamily {
+  template <bool DA, bool UH> using Dense = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, false>>;
+  template <bool DA, bool UH> using Gather = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, true>>;
+};
+// 2-D row marching: WPC warps per CTA, MINB CTAs per SM, PF rows of register prefetch
+template <class Phys, typename T, int P, int H, int WPC, int MINB, int PF>
+struct March2dFamily {
+  static constexpr int WIDE = Fv2dVec<T, Phys::NR + Phys::NA>::WIDE, NARROW = Fv2dVec<T, Phys::NR + Phys::NA>::NARROW;
+  template <bool DA, bool UH>
+  using Dense = Fv2dMarchDispatch<Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, UH, WIDE, PF, false>,
+                                  Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, UH, NARROW, PF, false>>;
+  template <bool DA, bool UH>
+  using Gather = Fv2dMarchLauncher<Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, UH, NARROW, PF, true>>;
+};
 
-// 2-D shape served by the row-marching kernel (WPC warps per CTA, register prefetch distance PF rows), with the thread-per-cell kernel (G, NT, MINB_CELL) as
-// alternative
-#define EXAHYPE_FV2D_ENTRY(MODEL, DTYPE, PHYS, T, P, H, WPC, MINB, PF, G, NT, MINB_CELL)                            \
-  {                                                                                                       \
-    {MODEL, DTYPE, 2, P, H, PHYS::NR, PHYS::NA, 0u},                                                      \
-        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, false)::launch,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, false)::launch,                               \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, true)::launch,                               \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, true)::launch},                               \
-        {&EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, false)::prepare,                             \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, false)::prepare,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, false, true)::prepare,                              \
-         &EXAHYPE_MARCH2D_DISPATCH(PHYS, T, P, H, WPC, MINB, PF, true, true)::prepare},                              \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, false)>::launch,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, false)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, true)>::launch,    \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, true)>::launch},    \
-        {&::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, false)>::prepare,  \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, false)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, false, true)>::prepare,   \
-         &::exahype::FvLauncher<EXAHYPE_FV_CFG(PHYS, T, 2, P, H, G, NT, MINB_CELL, true, true)>::prepare}    \
-  }
+// one kernel for the shape (thread per cell)
+template <class Cell>
+inline FvEntry cell_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
+  return make_entry<Cell::template Dense, Cell::template Gather, NoKernel>(model, dtype, dim, P, H, nr, na);
+}
+// marching kernel by default, thread-per-cell kernel behind EXAHYPE_FLAG_KERNEL_CELL
+template <class March, class Cell>
+inline FvEntry march_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
+  return make_entry<March::template Dense, March::template Gather, Cell::template Dense>(model, dtype, dim, P, H, nr, na);
+}
 
 }  // namespace exahype

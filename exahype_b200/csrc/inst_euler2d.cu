@@ -1,26 +1,32 @@
 // Committed instantiations: compressible Euler, 2-D (4 unknowns), fp64 and fp32.
-//   P = 3   BASELINE.json config C1 (3x3 + 1 halo, 1 000 patches): 28 patches per tile fill 252 threads
+//   P = 3   BASELINE.json config C1 (3x3 + 1 halo, 1 000 patches): thread per cell, 28 patches per tile fill 252 threads
 //   P = 16  config C2 (16x16 + 1 halo, 65 536 patches): row marching (fv2d_march_kernel.cuh), two patches per warp;
 //           alternative (EXAHYPE_FLAG_KERNEL_CELL): one patch per tile, one thread per interior cell
 //   P = 4 with 5 + 5 variables is the shape of the reference's committed kernel ("Unit test/test.cpp":4-8)
+#include <vector>
+
 #include "fv_registry.h"
 
 namespace exahype {
 namespace {
 using E2 = EulerPhysics<2, 4, 0>;
 using E2ref = EulerPhysics<2, 5, 5>;
+constexpr int EU = EXAHYPE_MODEL_EULER, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_DTYPE_F32;
 
-const FvEntry kEntries[] = {
-    // row-marching kernel (default): WPC warps per CTA, MINB, PF rows of register prefetch | thread-per-cell kernel: G, NT, MINB
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 16, 1, 4, 4, 2, 1, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E2, float, 16, 1, 4, 4, 3, 1, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 2, 3, 1, 28, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F32, E2, float, 2, 3, 1, 28, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 2, 4, 1, 16, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2, double, 8, 1, 4, 4, 2, 4, 256, 2),
-    EXAHYPE_FV_ENTRY(EXAHYPE_MODEL_EULER, EXAHYPE_DTYPE_F64, E2ref, double, 2, 4, 1, 8, 128, 2),
-};
+const std::vector<FvEntry>& entries() {
+  static const std::vector<FvEntry> v = {
+      //          row marching: phys, T, P, H, warps/CTA, CTAs/SM, PF | thread per cell: phys, T, dim, P, H, G, NT, CTAs/SM
+      march_entry<March2dFamily<E2, double, 16, 1, 4, 4, 2>, CellFamily<E2, double, 2, 16, 1, 1, 256, 2>>(EU, F64, 2, 16, 1, 4, 0),
+      march_entry<March2dFamily<E2, float, 16, 1, 4, 4, 3>, CellFamily<E2, float, 2, 16, 1, 1, 256, 2>>(EU, F32, 2, 16, 1, 4, 0),
+      march_entry<March2dFamily<E2, double, 8, 1, 4, 4, 2>, CellFamily<E2, double, 2, 8, 1, 4, 256, 2>>(EU, F64, 2, 8, 1, 4, 0),
+      cell_entry<CellFamily<E2, double, 2, 3, 1, 28, 256, 2>>(EU, F64, 2, 3, 1, 4, 0),
+      cell_entry<CellFamily<E2, float, 2, 3, 1, 28, 256, 2>>(EU, F32, 2, 3, 1, 4, 0),
+      cell_entry<CellFamily<E2, double, 2, 4, 1, 16, 256, 2>>(EU, F64, 2, 4, 1, 4, 0),
+      cell_entry<CellFamily<E2ref, double, 2, 4, 1, 8, 128, 2>>(EU, F64, 2, 4, 1, 5, 5),
+  };
+  return v;
+}
 }  // namespace
 
-FvEntryList euler2d_entries() { return {kEntries, (int)(sizeof(kEntries) / sizeof(kEntries[0]))}; }
+FvEntryList euler2d_entries() { return {entries().data(), (int)entries().size()}; }
 }  // namespace exahype

@@ -1,20 +1,26 @@
 // Committed instantiations: 2-D shallow water (h, hu, hv | bathymetry), fp64 and fp32.
 // BASELINE.json config C4: 32x32 patches + 1 halo -- row marching, one patch per warp (alternative: thread-per-cell,
 // 1024 interior cells, two per thread).
+#include <vector>
+
 #include "fv_registry.h"
 
 namespace exahype {
 namespace {
 using SW = SwePhysics<3, 1>;
+constexpr int SWE = EXAHYPE_MODEL_SWE, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_DTYPE_F32;
 
-const FvEntry kEntries[] = {
-    // row-marching kernel (default): WPC warps per CTA, MINB, PF rows of register prefetch | thread-per-cell kernel: G, NT, MINB
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 32, 1, 4, 4, 3, 1, 512, 1),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 32, 1, 4, 4, 3, 1, 512, 1),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F64, SW, double, 16, 1, 4, 4, 2, 1, 256, 2),
-    EXAHYPE_FV2D_ENTRY(EXAHYPE_MODEL_SWE, EXAHYPE_DTYPE_F32, SW, float, 16, 1, 4, 4, 3, 1, 256, 2),
-};
+const std::vector<FvEntry>& entries() {
+  static const std::vector<FvEntry> v = {
+      //          row marching: phys, T, P, H, warps/CTA, CTAs/SM, PF | thread per cell: phys, T, dim, P, H, G, NT, CTAs/SM
+      march_entry<March2dFamily<SW, double, 32, 1, 4, 4, 3>, CellFamily<SW, double, 2, 32, 1, 1, 512, 1>>(SWE, F64, 2, 32, 1, 3, 1),
+      march_entry<March2dFamily<SW, float, 32, 1, 4, 4, 3>, CellFamily<SW, float, 2, 32, 1, 1, 512, 1>>(SWE, F32, 2, 32, 1, 3, 1),
+      march_entry<March2dFamily<SW, double, 16, 1, 4, 4, 2>, CellFamily<SW, double, 2, 16, 1, 1, 256, 2>>(SWE, F64, 2, 16, 1, 3, 1),
+      march_entry<March2dFamily<SW, float, 16, 1, 4, 4, 3>, CellFamily<SW, float, 2, 16, 1, 1, 256, 2>>(SWE, F32, 2, 16, 1, 3, 1),
+  };
+  return v;
+}
 }  // namespace
 
-FvEntryList swe2d_entries() { return {kEntries, (int)(sizeof(kEntries) / sizeof(kEntries[0]))}; }
+FvEntryList swe2d_entries() { return {entries().data(), (int)entries().size()}; }
 }  // namespace exahype

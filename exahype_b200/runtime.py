@@ -44,6 +44,12 @@ class FvConfig(ctypes.Structure):
                 ("n_aux", ctypes.c_int32), ("flags", ctypes.c_uint32)]
 
 
+class CellData(ctypes.Structure):
+    """``exahype_cell_data`` of include/exahype_cuda.h (ExaHyPE2's ``CellData``: per-patch pointers and time steps)."""
+    _fields_ = [("n_patches", ctypes.c_int64), ("q_in", ctypes.c_void_p), ("q_out", ctypes.c_void_p),
+                ("dt", ctypes.c_void_p), ("max_eigenvalue", ctypes.c_void_p)]
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -65,6 +71,7 @@ def load(path: Optional[str] = None) -> ctypes.CDLL:
     lib.exahype_cuda_fv_supported.argtypes = [c_cfg]
     lib.exahype_cuda_fv_list.argtypes = [c_cfg, i32]
     lib.exahype_cuda_fv_step.argtypes = [c_cfg, vp, vp, i64, dbl, vp, vp, vp]
+    lib.exahype_cuda_fv_step_cell_data.argtypes = [c_cfg, ctypes.POINTER(CellData), dbl, vp, vp]
     lib.exahype_cuda_time_step_host.argtypes = [c_cfg, vp, vp, i64, dbl, vp, vp]
     lib.exahype_cuda_host_pipeline_configure.argtypes = [i64, i32]
     lib.exahype_cuda_launch_count.restype = i64
@@ -246,6 +253,34 @@ class PatchUpdate:
                 lambda_patch.data_ptr() if lambda_patch is not None else None,
                 lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
         return q_out
+
+    def step_cell_data(self, q_in_ptrs, q_out_ptrs, dt=0.0, dt_patch=None, max_eigenvalue=None, lambda_max=None,
+                       stream=None):
+        """The ``CellData`` form (``exahype_cuda_fv_step_cell_data``): ``q_in_ptrs`` / ``q_out_ptrs`` are CUDA int64
+        tensors of per-patch device pointers (``QIn`` haloed; ``QOut`` haloed or un-haloed per ``output``),
+        ``dt_patch`` an optional CUDA tensor of per-patch time steps, ``max_eigenvalue`` an optional per-patch output."""
+        import torch
+        tdt = torch.float64 if self.dtype == "f64" else torch.float32
+        n = int(q_in_ptrs.numel())
+        for name, t, want in (("q_in_ptrs", q_in_ptrs, torch.int64), ("q_out_ptrs", q_out_ptrs, torch.int64),
+                              ("dt_patch", dt_patch, tdt), ("max_eigenvalue", max_eigenvalue, tdt),
+                              ("lambda_max", lambda_max, tdt)):
+            if t is None:
+                continue
+            if not t.is_cuda or not t.is_contiguous() or t.dtype != want:
+                raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {want}")
+            if name not in ("lambda_max",) and t.numel() < n:
+                raise ValueError(f"{name} must hold one value per patch")
+        if stream is None:
+            stream = torch.cuda.current_stream(q_in_ptrs.device).cuda_stream
+        cells = CellData(n, q_in_ptrs.data_ptr(), q_out_ptrs.data_ptr(),
+                         dt_patch.data_ptr() if dt_patch is not None else None,
+                         max_eigenvalue.data_ptr() if max_eigenvalue is not None else None)
+        c = self.config()
+        with torch.cuda.device(q_in_ptrs.device):
+            check(self._lib.exahype_cuda_fv_step_cell_data(
+                ctypes.byref(c), ctypes.byref(cells), float(dt),
+                lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
 
     def fill_synthetic(self, q, first_patch: int = 0, seed: int = 20240601, stream=None):
         """Fills the CUDA tensor ``q`` (``in_shape(n)``) with the benchmark's synthetic admissible state for the global

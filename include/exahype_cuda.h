@@ -92,6 +92,28 @@ int exahype_cuda_fv_list(exahype_fv_config* out, int capacity);
 int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q_out, int64_t n_patches,
                          double dt, void* lambda_patch, void* lambda_max, void* stream);
 
+/*
+ * The ExaHyPE2 `CellData` form of the same step (reference examples/kernel-generator.py:8-19: `patchData` of type
+ * `::exahype2::CellData&` with members QIn, QOut, dt; the production boundary of Peano's
+ * timeStepWithRusanovBatchedStateless, "Unit test/correctness_test.cpp":138-163): the batch is not one dense array but a
+ * list of patches, each with its own pointers and its own time step.
+ *   q_in            device array of n_patches device pointers, each to one haloed patch S^dim * (n_real+n_aux), 16-byte aligned
+ *   q_out           device array of n_patches device pointers; q_out[p] == q_in[p] updates patch p in place (haloed),
+ *                   with EXAHYPE_FLAG_OUTPUT_UNHALOED each points to P^dim * (n_real+n_aux) values (CellData::QOut)
+ *   dt              device array of n_patches time steps of cfg->dtype (CellData::dt); null: the scalar `dt` argument
+ *   max_eigenvalue  device array of n_patches, nullable (CellData::maxEigenvalue): as lambda_patch of exahype_cuda_fv_step
+ */
+typedef struct {
+  int64_t n_patches;
+  const void* const* q_in;
+  void* const* q_out;
+  const void* dt;
+  void* max_eigenvalue;
+} exahype_cell_data;
+
+int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_cell_data* cells, double dt,
+                                   void* lambda_max, void* stream);
+
 /* Named entry points for the committed headline instantiations (same semantics as exahype_cuda_fv_step). */
 int exahype_cuda_fv_step_euler_2d_f64(const double* q_in, double* q_out, int64_t n_patches, int patch_size, int halo,
                                       int n_aux, double dt, double* lambda_patch, double* lambda_max,

@@ -298,6 +298,59 @@ def test_errors_on_device(torch, rt):
     assert rt.launch_count() == before + 1
 
 
+# ----------------------------------------------------------------------------------------- CellData form
+@pytest.mark.parametrize("model,dim,P,nr,na,dtype", [
+    ("euler", 3, 8, 5, 0, "f64"), ("euler", 3, 4, 5, 0, "f32"), ("euler", 2, 16, 4, 0, "f64"), ("euler", 2, 3, 4, 0, "f64"),
+    ("euler", 2, 4, 5, 5, "f64"), ("swe", 2, 32, 3, 1, "f32"), ("swe", 2, 32, 3, 1, "f64")])
+@pytest.mark.parametrize("output", ["haloed", "unhaloed"])
+def test_cell_data_form_gathered_patches_and_per_patch_dt(torch, rt, oracle, model, dim, P, nr, na, dtype, output):
+    """exahype_cuda_fv_step_cell_data: patches scattered through a pool in permuted order (QIn[p] / QOut[p] pointers),
+    each with its own dt (CellData::dt), per-patch eigenvalue into CellData::maxEigenvalue.  Every patch must equal the
+    oracle run on that patch alone with that dt, bit for bit; the pool outside the addressed patches stays untouched."""
+    upd = rt.PatchUpdate(model, dim, P, 1, nr, na, dtype=dtype, output=output, dissipation="all")
+    cfg = oracle_cfg(oracle, upd)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    npdt = np.float64 if dtype == "f64" else np.float32
+    n, pool_n = 45, 64
+    rng = np.random.default_rng(7)
+    slots = rng.permutation(pool_n)[:n]                     # patch p lives in pool slot slots[p]
+    dts = rng.uniform(0.002, 0.02, n).astype(npdt)
+    q0 = oracle.fill_synthetic(cfg, n, dtype=npdt)
+    pool = torch.full(upd.in_shape(pool_n), -5.0, dtype=tdt, device="cuda")
+    pool[torch.from_numpy(slots).cuda()] = torch.from_numpy(q0).cuda()
+    per_in = int(np.prod(upd.in_shape(1))) * pool.element_size()
+    in_ptrs = torch.tensor([pool.data_ptr() + int(s) * per_in for s in slots], dtype=torch.int64, device="cuda")
+    if output == "haloed":
+        out_pool, out_ptrs = pool, in_ptrs                  # in place, the reference's semantics
+    else:
+        out_pool = torch.full(upd.out_shape(pool_n), -7.0, dtype=tdt, device="cuda")
+        per_out = int(np.prod(upd.out_shape(1))) * out_pool.element_size()
+        out_slots = rng.permutation(pool_n)[:n]
+        out_ptrs = torch.tensor([out_pool.data_ptr() + int(s) * per_out for s in out_slots], dtype=torch.int64, device="cuda")
+    lam = torch.zeros(n, dtype=tdt, device="cuda")
+    lmax = torch.zeros(1, dtype=tdt, device="cuda")
+    upd.step_cell_data(in_ptrs, out_ptrs, dt_patch=torch.from_numpy(dts).cuda(), max_eigenvalue=lam, lambda_max=lmax)
+    torch.cuda.synchronize()
+    want = q0.copy()
+    lam_o = np.zeros(n, dtype=npdt)
+    for p in range(n):
+        one = want[p:p + 1]
+        l, _ = oracle.step(cfg, one, float(dts[p]))
+        lam_o[p] = l[0]
+    assert_bitwise(lam.cpu().numpy(), lam_o, "maxEigenvalue")
+    assert float(lmax.item()) == float(lam_o.max())
+    out_np = out_pool.cpu().numpy()
+    if output == "haloed":
+        assert_bitwise(out_np[slots], want, "in-place patches")
+        untouched = np.setdiff1d(np.arange(pool_n), slots)
+        assert (out_np[untouched] == -5.0).all()
+    else:
+        assert_bitwise(out_np[out_slots], interior(upd, want), "QOut patches")
+        untouched = np.setdiff1d(np.arange(pool_n), out_slots)
+        assert (out_np[untouched] == -7.0).all()
+        assert_bitwise(pool.cpu().numpy()[slots], q0, "QIn untouched")
+
+
 # ----------------------------------------------------------------------------------------- BASELINE sizes
 @pytest.mark.parametrize("model,dim,P,nr,na,n", [("euler", 3, 8, 5, 0, 32768), ("euler", 2, 16, 4, 0, 65536),
                                                  ("swe", 2, 32, 3, 1, 16384)])
