@@ -32,17 +32,42 @@ def rt():
     return runtime
 
 
+GUARD = 512          # elements of sentinel on either side of every device buffer the kernels write
+SENTINEL = -977.0
+
+
+def guarded(torch, shape, tdt, fill=None):
+    """A device tensor of `shape` carved out of a larger allocation whose margins hold a sentinel: a kernel that writes
+    outside its buffers (compute-sanitizer is closed on this GPU pool) trips check_guards()."""
+    n = int(np.prod(shape))
+    raw = torch.full((n + 2 * GUARD,), SENTINEL, dtype=tdt, device="cuda")
+    view = raw[GUARD:GUARD + n].view(shape)
+    if fill is not None:
+        view.fill_(fill)
+    return raw, view
+
+
+def check_guards(raws):
+    for raw in raws:
+        assert bool((raw[:GUARD] == SENTINEL).all()) and bool((raw[-GUARD:] == SENTINEL).all()), "write outside a buffer"
+
+
 def gpu_step(torch, upd, q_np, dt, out=None, want_lambda=True):
-    """Runs one step on the device; returns (q_out numpy, lambda_patch numpy, lambda_max)."""
+    """Runs one step on the device; returns (q_out numpy, lambda_patch numpy, lambda_max).  Every buffer sits between
+    sentinel guard bands that are verified after the launch."""
     tdt = torch.float64 if upd.dtype == "f64" else torch.float32
-    q = torch.from_numpy(q_np).cuda()
     n = q_np.shape[0]
-    lam = torch.full((n,), -1.0, dtype=tdt, device="cuda")
-    lmax = torch.full((1,), -1.0, dtype=tdt, device="cuda")
+    raw_q, q = guarded(torch, q_np.shape, tdt)
+    q.copy_(torch.from_numpy(q_np))
+    raw_l, lam = guarded(torch, (n,), tdt, -1.0)
+    raw_m, lmax = guarded(torch, (1,), tdt, -1.0)
+    raws = [raw_q, raw_l, raw_m]
     if upd.output == "unhaloed":
-        out = torch.full(upd.out_shape(n), 7.0, dtype=tdt, device="cuda")
+        raw_o, out = guarded(torch, upd.out_shape(n), tdt, 7.0)
+        raws.append(raw_o)
     res = upd.step(q, out, dt, lam if want_lambda else None, lmax if want_lambda else None)
     torch.cuda.synchronize()
+    check_guards(raws)
     return res.cpu().numpy(), lam.cpu().numpy(), float(lmax.item())
 
 
