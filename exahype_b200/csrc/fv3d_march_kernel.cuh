@@ -22,6 +22,8 @@
 //     segments.
 #pragma once
 
+#include <type_traits>
+
 #include "fv_patch_kernel.cuh"
 
 namespace exahype {
@@ -46,6 +48,12 @@ struct Fv3dMarchConfig {
   static constexpr int OUT_PLANE_ELEMS = P * P * NV;
   static constexpr int OUT_PATCH_ELEMS = P * OUT_PLANE_ELEMS;
   static_assert(PLANE_BYTES % 16 == 0, "plane must be a whole number of 16-byte units for TMA bulk copies");
+  // the two halo planes of a patch are only read at interior (j, k): their rows H .. H+P-1 are one contiguous run, and
+  // the copy skips the rest when that run keeps the 16-byte granularity of bulk copies
+  static constexpr int ROW_BYTES = S * NV * (int)sizeof(T);
+  static constexpr bool TRIM_HALO_PLANES = (ROW_BYTES % 16 == 0);
+  static constexpr int HALO_PLANE_SKIP_ELEMS = TRIM_HALO_PLANES ? H * S * NV : 0;
+  static constexpr int HALO_PLANE_BYTES = TRIM_HALO_PLANES ? P * ROW_BYTES : PLANE_BYTES;
 
   static constexpr int N_INT = P * P;                     // interior columns
   static constexpr int N_FACE = 4 * P;                    // face-halo columns of axes 1 and 2
@@ -97,6 +105,11 @@ struct Fv3dMarchConfig {
   }
 };
 
+template <class Phys, typename T, class = void>
+struct has_runtime_axis : std::false_type {};
+template <class Phys, typename T>
+struct has_runtime_axis<Phys, T, std::void_t<decltype(&Phys::template eigen_runtime<T>)>> : std::true_type {};
+
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -129,10 +142,13 @@ struct MarchStream {
   // parameter itself, read from the constant bank where it is used instead of occupying registers
   __device__ __forceinline__ void issue_next_load(const FvGather<T>& gather) {
     const long long patch = g_index + (long long)p_pi * n_groups;
-    mbar_expect_tx(&full[p_slot], C::PLANE_BYTES);
-    tma_load_1d(ring + p_slot * C::PLANE_ELEMS,
-                gather.template in<C::GATHER>(q_in, patch, C::PATCH_ELEMS) + (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS,
-                C::PLANE_BYTES, &full[p_slot]);
+    const bool halo_plane = (p_ip == 0) || (p_ip == C::NPL - 1);
+    const int skip = halo_plane ? C::HALO_PLANE_SKIP_ELEMS : 0;
+    const uint32_t bytes = halo_plane ? C::HALO_PLANE_BYTES : C::PLANE_BYTES;
+    mbar_expect_tx(&full[p_slot], bytes);
+    tma_load_1d(ring + p_slot * C::PLANE_ELEMS + skip,
+                gather.template in<C::GATHER>(q_in, patch, C::PATCH_ELEMS) + (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS + skip,
+                bytes, &full[p_slot]);
     ++p_seq;
     if (++p_ip == C::NPL) { p_ip = 0; ++p_pi; }
     if (++p_slot == C::R) p_slot = 0;
@@ -325,10 +341,14 @@ __device__ __forceinline__ void march_interior_patch(MarchStream<C>& ms, const F
   march_interior_step<C, (C::P + 1) % 3, MARCH_LAST>(ms, gather, C::P + 1, a...);
 }
 
-// One plane for a face-halo column of axis AXIS (1 or 2): F_AXIS and L_AXIS of the cell one layer outside the interior.
-template <class C, int AXIS>
+// One plane for a face-halo column of axis 1 or 2: F_axis and L_axis of the cell one layer outside the interior.
+// `axis` differs between the lanes of the face warp (f = [axis-1 low | axis-1 high | axis-2 low | axis-2 high]); both are
+// evaluated by ONE instruction stream -- the flux of either axis is the same arithmetic on a different momentum
+// component (physics.cuh: flux_runtime / eigen_runtime), selected per lane -- instead of two divergent halves.
+template <class C>
 __device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const typename C::T* __restrict__ qs, int cell,
-                                                int slot_in_scratch, int buf) {
+                                                int axis, typename C::T* __restrict__ Fw, typename C::T* __restrict__ Lw,
+                                                int comp_stride) {
   using T = typename C::T;
   using Phys = typename C::Phys;
   T q[C::NV];
@@ -336,13 +356,20 @@ __device__ __forceinline__ void march_face_eval(const MarchStream<C>& ms, const 
   for (int v = 0; v < C::NV; ++v) q[v] = qs[cell * C::NV + v];
   const auto pr = Phys::template prims<T>(q);
   T F[C::NR];
-  Phys::template flux<AXIS, T>(q, pr, F);
-  T* Fs = (AXIS == 1) ? ms.Fj : ms.Fk;
-  T* Ls = (AXIS == 1) ? ms.Lj : ms.Lk;
-  constexpr int SX = (AXIS == 1) ? C::SJ : C::SK;
+  T L;
+  if constexpr (has_runtime_axis<Phys, T>::value) {
+    Phys::template flux_runtime<T>(q, pr, axis, F);
+    L = Phys::template eigen_runtime<T>(q, pr, axis);
+  } else if (axis == 1) {     // functors without the run-time forms (generated from SymPy / user source): two divergent halves
+    Phys::template flux<1, T>(q, pr, F);
+    L = Phys::template eigen<1, T>(q, pr);
+  } else {
+    Phys::template flux<2, T>(q, pr, F);
+    L = Phys::template eigen<2, T>(q, pr);
+  }
 #pragma unroll
-  for (int v = 0; v < C::NR; ++v) Fs[(buf * C::NR + v) * SX + slot_in_scratch] = F[v];
-  Ls[buf * SX + slot_in_scratch] = Phys::template eigen<AXIS, T>(q, pr);
+  for (int v = 0; v < C::NR; ++v) Fw[v * comp_stride] = F[v];
+  *Lw = L;
 }
 
 template <class C>
@@ -431,13 +458,17 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     const int cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
     const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos
                                               : f_pos * C::PK + (f_side ? P + 1 : 0);
+    // per lane: where this column's F / L go in the scratch of its axis (buffer 0; buffer 1 is one buffer further)
+    T* const F_base = (f_axis == 1 ? ms.Fj : ms.Fk) + slot_in_scratch;
+    T* const L_base = (f_axis == 1 ? ms.Lj : ms.Lk) + slot_in_scratch;
+    const int comp_stride = (f_axis == 1) ? C::SJ : C::SK;
     for (; ms.pi < ms.n_my_patches; ++ms.pi) {
       for (int ip = 0; ip < NPL; ++ip) {
         if (ip >= 1 && ip <= P) {          // halo planes need no axis-1/2 fluxes: the face warps do not even wait for them
           const T* __restrict__ qs = ms.wait_plane();
           if (live) {
-            if (f_axis == 1) march_face_eval<C, 1>(ms, qs, cell, slot_in_scratch, ip & 1);
-            else march_face_eval<C, 2>(ms, qs, cell, slot_in_scratch, ip & 1);
+            const int buf = ip & 1;
+            march_face_eval<C>(ms, qs, cell, f_axis, F_base + buf * (NR * comp_stride), L_base + buf * comp_stride, comp_stride);
           }
         }
         named_barrier_sync(ms.bar_id, C::GROUP_THREADS);
