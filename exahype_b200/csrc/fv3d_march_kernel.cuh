@@ -84,7 +84,7 @@ struct Fv3dMarchConfig {
   static constexpr int OFF_STAGE = align_up(OFF_LK + 2 * SK * (int)sizeof(T), 128);
   static constexpr int OFF_LAM = align_up(OFF_STAGE + 2 * STAGE_SEGS * SEG_PITCH * (int)sizeof(T), 16);
   static constexpr int OFF_BAR = align_up(OFF_LAM + 2 * 8, 16);
-  static constexpr int GROUP_BYTES = align_up(OFF_BAR + R * 8, 128);
+  static constexpr int GROUP_BYTES = align_up(OFF_BAR + R * 8, 16);
   static constexpr int SMEM_BYTES = NG * GROUP_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "groups do not fit the 227 KB of shared memory per CTA");
 

@@ -14,11 +14,14 @@ constexpr int EU = EXAHYPE_MODEL_EULER, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_D
 #ifndef EXAHYPE_3D_NG
 #define EXAHYPE_3D_NG 5   // warp groups per CTA of the plane-marching kernel for 8^3 patches
 #endif
+#ifndef EXAHYPE_3D_R
+#define EXAHYPE_3D_R 5    // planes in each group's TMA ring
+#endif
 
 const std::vector<FvEntry>& entries() {
   static const std::vector<FvEntry> v = {
       //          plane marching: phys, T, P, H, NG groups, R planes, CTAs/SM | thread per cell: phys, T, dim, P, H, G, NT, CTAs/SM
-      march_entry<March3dFamily<E3, double, 8, 1, EXAHYPE_3D_NG, 5, 1>, CellFamily<E3, double, 3, 8, 1, 1, 512, 1>>(EU, F64, 3, 8, 1, 5, 0),
+      march_entry<March3dFamily<E3, double, 8, 1, EXAHYPE_3D_NG, EXAHYPE_3D_R, 1>, CellFamily<E3, double, 3, 8, 1, 1, 512, 1>>(EU, F64, 3, 8, 1, 5, 0),
       march_entry<March3dFamily<E3, float, 8, 1, 5, 5, 1>, CellFamily<E3, float, 3, 8, 1, 1, 512, 1>>(EU, F32, 3, 8, 1, 5, 0),
       march_entry<March3dFamily<E3, double, 4, 1, 6, 6, 1>, CellFamily<E3, double, 3, 4, 1, 4, 256, 2>>(EU, F64, 3, 4, 1, 5, 0),
       march_entry<March3dFamily<E3, float, 4, 1, 6, 6, 1>, CellFamily<E3, float, 3, 4, 1, 4, 256, 2>>(EU, F32, 3, 4, 1, 5, 0),
