@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the kernel-only timings of the other BASELINE workloads")
     ap.add_argument("--variants", action="store_true", help="also time the other output/dissipation variants and workloads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -311,6 +312,18 @@ def main():
     variants = None
     if args.variants and world == 1:
         variants = time_variants(torch, runtime, args)
+    # the other BASELINE configurations next to the headline one (kernel-only, a few ms each): parity-test cases, not
+    # bench lines, reported so that one run shows every committed kernel family against the same roofline
+    others = None
+    if world == 1 and not args.no_others:
+        peak_gbs, _ = measured_hbm_peak()
+        others = {}
+        for wl in ("c2", "c4", "c4f32"):
+            if wl == args.workload:
+                continue
+            r = time_kernel_only(torch, runtime, wl)
+            others[wl] = {"workload": WORKLOADS[wl][8], "kernel_ms": r["ms"], "value": r["cell_updates_per_s"],
+                          "achieved_GBs": r["algorithmic_GBs"], "frac": r["algorithmic_GBs"] / peak_gbs}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -338,6 +351,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if others is not None:
+            line["other_workloads"] = others
         if variants is not None:
             line["variants"] = variants
         if not args.no_cpu and world >= 1:
@@ -360,34 +375,38 @@ def synthetic_on_device(torch, upd, first_patch: int, n_patches: int, tdt, devic
     return upd.fill_synthetic(q, first_patch)
 
 
+def time_kernel_only(torch, runtime, wl, output="unhaloed", diss="var0", kern="auto", steps=10):
+    """Kernel-only timing of one committed variant on its BASELINE batch (same timing hygiene as the main loop: warm-up,
+    CUDA events on the launching stream, inputs larger than L2)."""
+    model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output, kernel=kern)
+    q_in = synthetic_on_device(torch, upd, 0, batch, tdt)
+    q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
+    lam = torch.zeros(1, dtype=tdt, device="cuda")
+    for _ in range(3):
+        upd.step(q_in, q_out, 0.01, None, lam)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        upd.step(q_in, q_out, 0.01, None, lam)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    gbs = upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9
+    return {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3), "algorithmic_GBs": gbs}
+
+
 def time_variants(torch, runtime, args):
     """Kernel-only timings of the other committed variants / workloads (informative; same timing hygiene)."""
-    import numpy as np
     res = {}
     for wl in ("c3", "c2", "c4", "c4f32", "c1"):
-        model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
-        tdt = torch.float64 if dtype == "f64" else torch.float32
+        dim = WORKLOADS[wl][1]
         for output, diss, kern in [(o, d, k) for o in ("unhaloed", "haloed") for d in ("var0", "all")
                                    for k in (("auto", "cell") if dim == 3 else ("auto",))]:
-            if True:
-                upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output=output, kernel=kern)
-                q_in = synthetic_on_device(torch, upd, 0, batch, tdt)
-                q_out = torch.empty(upd.out_shape(batch), dtype=tdt, device="cuda")
-                lam = torch.zeros(1, dtype=tdt, device="cuda")
-                for _ in range(3):
-                    upd.step(q_in, q_out, 0.01, None, lam)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                a.record()
-                for _ in range(10):
-                    upd.step(q_in, q_out, 0.01, None, lam)
-                b.record()
-                torch.cuda.synchronize()
-                ms = a.elapsed_time(b) / 10
-                gbs = upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9
-                res[f"{wl}/{output}/{diss}" + ("/cell-kernel" if kern == "cell" else "")] = {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3),
-                                                "algorithmic_GBs": gbs}
-                del q_in, q_out
+            res[f"{wl}/{output}/{diss}" + ("/cell-kernel" if kern == "cell" else "")] = \
+                time_kernel_only(torch, runtime, wl, output, diss, kern)
     # the CellData form (per-patch pointers + per-patch dt) on the headline workload: same kernel, gathered addressing
     for wl in ("c3", "c2"):
         model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]

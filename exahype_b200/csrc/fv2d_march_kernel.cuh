@@ -9,9 +9,10 @@
 //   * lane <-> (patch of the warp, interior column k).  A row of P cells of one patch is one contiguous run of the AoS
 //     batch, a cell of 4 fp64 variables is exactly one 32-byte sector: every lane loads ITS cell straight from HBM into
 //     registers with one 256-bit load (LDG.E.256, or 128-bit loads when the buffers are only 16-byte aligned) and stores
-//     its updated cell with one 256-bit store.  Loads run PF = 2 rows ahead of the row being consumed.
-//   * the axis-0 stencil lives in registers: rolling window {r-2, r-1, r} of the cell state, F_0 and L_0 (ring of 4 rows,
-//     row loop unrolled by 4 so every ring index is a compile-time constant).
+//     its updated cell with one 256-bit store.  Loads run PF (2 or 3) rows ahead of the row being consumed, and a bulk L2
+//     prefetch (cp.async.bulk.prefetch.L2, one lane per patch, no registers) runs 2 KB ahead of those.
+//   * the axis-0 stencil lives in registers: rolling window {r-2, r-1, r} of the cell state, F_0 and L_0 (ring of PF+2
+//     rows, row loop unrolled by the ring size so every ring index is a compile-time constant).
 //   * only F_1, L_1 and the DV dissipated variables of the row cross lanes, through a warp-private double-buffered
 //     shared row (conflict-free SoA, one __syncwarp per row; no CTA barriers, no mbarriers, no named barriers).
 //   * the 2*P face-halo cells of axis 1 of each patch (one layer left and right of every interior row) are evaluated
@@ -19,8 +20,8 @@
 //     of the shared row.  Halo corners are never touched (they are not inputs).
 //   * per-patch max eigenvalue: running maximum in registers, segmented warp-shuffle reduction at the end of the patch.
 //
-// Shared memory: COMPS * 128 values per warp (6 KB for Euler fp64 var0), registers ~100: ~16-20 independent warps per SM,
-// each streaming rows of 512-1024 contiguous bytes.
+// Shared memory: COMPS * 128 values per warp (6 KB for Euler fp64 var0), 128 registers: 16 independent warps per SM, each
+// streaming rows of 512-1024 contiguous bytes.  Measured: C2 0.22 ms, C4 0.72 ms (83-86 % of the measured HBM copy peak).
 #pragma once
 
 #include "fv_patch_kernel.cuh"
