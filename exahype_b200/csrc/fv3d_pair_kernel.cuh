@@ -1,0 +1,490 @@
+// sm_100a warp-per-patch plane-marching kernel for the 3-D batched stateless FV Rusanov patch update, 8x8x8 patches.
+//
+// Same arithmetic, statement order and results as fv_patch_kernel.cuh / fv3d_march_kernel.cuh (reference
+// "Unit test/test.cpp":11-104 with the loop ranges of exahype/printers/CPPPrinter.py:116-137).  The group-of-three-warps
+// kernel (fv3d_march_kernel.cuh) spends 29 % of its warp samples at the group's named barrier, a third of its warps
+// (the face warps) idle, and its interior threads run one dependent fp64 chain each (profiles/r01_ncu_c3_march.txt:
+// stall_wait 26 %).  Here ONE WARP owns a patch and marches through its planes along axis 0:
+//
+//   * lane <-> two vertically adjacent columns (rows 2jp and 2jp+1, same k) plus one of the 32 face-halo columns: three
+//     independent instruction chains per lane, and the axis-1 exchange between the two rows never leaves registers;
+//   * the axis-0 stencil is a rolling register window {i-1, i, i+1} of state, F_0, L_0 and the per-cell primitives;
+//   * the step for plane i loads plane i+1 (its F_0 / L_0 complete the axis-0 stencil of plane i), evaluates F_1, F_2,
+//     L_1, L_2 of plane i, publishes what other lanes need in warp-private shared scratch, and updates plane i in the same
+//     step: nothing but the window is carried from plane to plane, the scratch is single buffered;
+//   * all synchronisation is __syncwarp (two per plane).  Warps are independent: no named barriers, no CTA barrier after
+//     start-up, every warp has its own TMA ring (1-D bulk copies + mbarrier complete_tx), scratch and output staging;
+//   * finished planes leave through a two-deep staging buffer and TMA bulk stores, as in fv3d_march_kernel.cuh.
+//
+// Bank-conflict-free for fp64: a half-warp holds row pairs {0, 2} or {1, 3} (rows 0/1 and 4/5, resp. 2/3 and 6/7), the
+// AoS plane has a cell stride of 5 doubles, scratch rows are pitched 10, the staging buffer is two padded segments.
+#pragma once
+
+#include "fv3d_march_kernel.cuh"
+
+namespace exahype {
+
+__device__ __forceinline__ void tma_store_wait_read_all_but_one() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+
+template <class Phys_, class Upd_, typename T_, int P_, int H_, int NW_, int R_, bool DISS_ALL_, bool UNHALOED_,
+          bool GATHER_ = false>
+struct Fv3dPairConfig {
+  using Phys = Phys_;
+  using Upd = Upd_;
+  using T = T_;
+  static constexpr int DIM = 3, P = P_, H = H_, NW = NW_, R = R_;
+  static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_, GATHER = GATHER_;
+  static_assert(P == 8 && H == 1, "one warp per 8x8 plane: 32 row pairs and 32 face-halo columns");
+  static_assert(NW >= 1 && NW <= 32 && R >= 3, "pair-march geometry");
+
+  static constexpr int NR = Phys::NR, NA = Phys::NA, NV = NR + NA;
+  static constexpr int S = P + 2 * H;
+  static constexpr int NPL = P + 2;
+  static constexpr int PLANE_ELEMS = S * S * NV;
+  static constexpr int PLANE_BYTES = PLANE_ELEMS * (int)sizeof(T);
+  static constexpr int PATCH_ELEMS = S * PLANE_ELEMS;
+  static constexpr int OUT_PLANE_ELEMS = P * P * NV;
+  static constexpr int OUT_PATCH_ELEMS = P * OUT_PLANE_ELEMS;
+  static_assert(PLANE_BYTES % 16 == 0, "plane must be a whole number of 16-byte units for TMA bulk copies");
+  // the two halo planes of a patch are only read at interior (j, k): rows H .. H+P-1 are one contiguous run
+  static constexpr int ROW_BYTES = S * NV * (int)sizeof(T);
+  static constexpr bool TRIM_HALO_PLANES = (ROW_BYTES % 16 == 0);
+  static constexpr int HALO_PLANE_SKIP_ELEMS = TRIM_HALO_PLANES ? H * S * NV : 0;
+  static constexpr int HALO_PLANE_BYTES = TRIM_HALO_PLANES ? P * ROW_BYTES : PLANE_BYTES;
+
+  static constexpr int NT = NW * 32;
+  static constexpr int DV = DISS_ALL ? NR : 1;
+
+  static constexpr int PJ = 10;                     // F_1 scratch: [x_j in 0..P+1][k], pitch PJ
+  static constexpr int PK = P + 2;                  // F_2 scratch: [j][x_k in 0..P+1], pitch PK
+  static constexpr int SJ = (P + 2) * PJ;
+  static constexpr int SK = P * PK;
+  static constexpr int SEG_ELEMS = OUT_PLANE_ELEMS / 2;                 // staging: rows j < 4 | j >= 4
+  static constexpr int SEG_PITCH = SEG_ELEMS + 64 / (int)sizeof(T);     // +64 bytes
+  static constexpr int STAGE_ELEMS = 2 * SEG_PITCH;
+  static constexpr bool USE_TMA_STORE = UNHALOED && ((SEG_ELEMS * (int)sizeof(T)) % 16 == 0) &&
+                                        ((SEG_PITCH * (int)sizeof(T)) % 16 == 0);
+
+  // per-warp shared memory
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_FJ = align_up(OFF_RING + R * PLANE_BYTES, 16);
+  static constexpr int OFF_FK = align_up(OFF_FJ + NR * SJ * (int)sizeof(T), 16);
+  static constexpr int OFF_LJ = align_up(OFF_FK + NR * SK * (int)sizeof(T), 16);
+  static constexpr int OFF_LK = align_up(OFF_LJ + SJ * (int)sizeof(T), 16);
+  static constexpr int OFF_STAGE = align_up(OFF_LK + SK * (int)sizeof(T), 128);
+  static constexpr int OFF_BAR = align_up(OFF_STAGE + 2 * STAGE_ELEMS * (int)sizeof(T), 16);
+  static constexpr int WARP_BYTES = align_up(OFF_BAR + R * 8, 128);
+  static constexpr int SMEM_BYTES = NW * WARP_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "warps do not fit the 227 KB of shared memory per CTA");
+
+  static __device__ __forceinline__ int stage_index(int j, int k) {     // element offset of cell (j,k), variable 0
+    return (j >> 2) * SEG_PITCH + ((j & 3) * P + k) * NV;
+  }
+};
+
+// Per-lane view of one warp's stream of planes: plane n of the stream lives in ring slot n % R.
+template <class C>
+struct PairStream {
+  using T = typename C::T;
+  const T* q_in;
+  T* q_out;
+  T* lambda_patch;
+  T *ring, *Fj, *Fk, *Lj, *Lk, *stage;
+  unsigned long long* full;
+  long long w_index, n_warps;
+  T dt;
+  int n_seq;          // planes this warp streams = patches * (P+2)
+  int n_my_patches;
+  int lane;
+  int pi, slot;       // consumer cursor: patch counter, ring slot (+ mbarrier phase parity) of the next plane
+  uint32_t parity;
+  int p_seq, p_ip, p_pi, p_slot;   // producer cursor (lane 0): next plane to request
+
+  __device__ __forceinline__ long long patch_of(int i) const { return w_index + (long long)i * n_warps; }
+
+  __device__ __forceinline__ void issue_next_load(const FvGather<T>& gather) {
+    const bool halo_plane = (p_ip == 0) || (p_ip == C::NPL - 1);
+    const int skip = halo_plane ? C::HALO_PLANE_SKIP_ELEMS : 0;
+    const uint32_t bytes = halo_plane ? C::HALO_PLANE_BYTES : C::PLANE_BYTES;
+    mbar_expect_tx(&full[p_slot], bytes);
+    tma_load_1d(ring + p_slot * C::PLANE_ELEMS + skip,
+                gather.template in<C::GATHER>(q_in, patch_of(p_pi), C::PATCH_ELEMS) +
+                    (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS + skip,
+                bytes, &full[p_slot]);
+    ++p_seq;
+    if (++p_ip == C::NPL) { p_ip = 0; ++p_pi; }
+    if (++p_slot == C::R) p_slot = 0;
+  }
+  __device__ __forceinline__ const T* wait_plane() {
+    mbar_wait(&full[slot], parity);
+    return ring + slot * C::PLANE_ELEMS;
+  }
+  __device__ __forceinline__ const T* previous_plane() const {
+    return ring + (slot == 0 ? C::R - 1 : slot - 1) * C::PLANE_ELEMS;
+  }
+  __device__ __forceinline__ void advance_plane() {
+    if (++slot == C::R) { slot = 0; parity ^= 1u; }
+  }
+
+  // After the closing __syncwarp of a step: write out zero-based interior plane `plane` of patch pi from staging `buffer`.
+  __device__ __forceinline__ void drain_staged_plane(const FvGather<T>& gather, int plane, int buffer) {
+    const long long patch = patch_of(pi);
+    const T* sbuf = stage + buffer * C::STAGE_ELEMS;
+    if (C::UNHALOED) {
+      T* dst = gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + (long long)plane * C::OUT_PLANE_ELEMS;
+      if (C::USE_TMA_STORE) {
+        if (lane == 0) {
+          tma_store_1d(dst, sbuf, C::SEG_ELEMS * (uint32_t)sizeof(T));
+          tma_store_1d(dst + C::SEG_ELEMS, sbuf + C::SEG_PITCH, C::SEG_ELEMS * (uint32_t)sizeof(T));
+          tma_store_commit();
+          tma_store_wait_read_all_but_one();    // the other staging buffer (written next step) is free again
+        }
+      } else {
+        for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
+          const int sgm = e / C::SEG_ELEMS;
+          dst[e] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+        }
+      }
+    } else {
+      // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
+      T* dst = gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + (long long)(plane + C::H) * C::PLANE_ELEMS;
+      constexpr int ROW = C::P * C::NV;
+      for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
+        const int row = e / ROW;
+        const int sgm = e / C::SEG_ELEMS;
+        dst[((row + C::H) * C::S + C::H) * C::NV + (e - row * ROW)] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+      }
+    }
+  }
+};
+
+// what a lane owns: the cells (ja, k) and (ja + 1, k) of every plane and one face-halo column of axis 1 or 2
+template <class C>
+struct PairLane {
+  using T = typename C::T;
+  int cell;          // haloed in-plane cell index of (ja, k); the partner row is cell + S
+  int sj, sk;        // scratch slots of (ja, k): partner row at sj + PJ / sk + PK
+  int st;            // staging offsets of (ja, k); the partner row is st + P*NV (same segment)
+  int f_cell, f_axis, f_comp_stride;
+  T *f_F, *f_L;      // where the face column's F / L go
+};
+
+// the axis-0 window of one lane: three planes x two cells, all indices compile-time
+template <class C>
+struct PairWindow {
+  using T = typename C::T;
+  using Prims = typename C::Phys::template Prims<T>;
+  T q[3][2][C::NV];
+  T fi[3][2][C::NR];
+  T li[3][2];
+  Prims pr[3][2];
+};
+
+// plane `W` of the window <- the plane the stream delivers next: state, primitives, F_0, L_0
+template <class C, int W>
+__device__ __forceinline__ void pair_load_plane(PairStream<C>& ps, const PairLane<C>& ln, PairWindow<C>& w) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  const T* __restrict__ qs = ps.wait_plane();
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int v = 0; v < C::NV; ++v) w.q[W][c][v] = qs[(ln.cell + c * C::S) * C::NV + v];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    w.pr[W][c] = Phys::template prims<T>(w.q[W][c]);
+    Phys::template flux<0, T>(w.q[W][c], w.pr[W][c], w.fi[W][c]);
+    w.li[W][c] = Phys::template eigen<0, T>(w.q[W][c], w.pr[W][c]);
+  }
+}
+
+// the first two planes of a patch (halo plane 0, interior plane 1) only fill the window
+template <class C, int W>
+__device__ __forceinline__ void pair_pre_step(PairStream<C>& ps, const FvGather<typename C::T>& gather,
+                                              const PairLane<C>& ln, PairWindow<C>& w) {
+  pair_load_plane<C, W>(ps, ln, w);
+  // The slot requested next is that of the previous plane of the stream.  W == 0: the last plane of the previous patch,
+  // last read before the closing __syncwarp of the previous step.  W == 1: plane 0, which every lane has read once the
+  // warp meets here (halo planes are never read from the ring again).
+  if (W == 1) __syncwarp();
+  if (ps.lane == 0 && (W == 1 || ps.pi >= 1) && ps.p_seq < ps.n_seq) ps.issue_next_load(gather);
+  ps.advance_plane();
+}
+
+// Interior plane ip (1..P) of the current patch, window phase PH = ip % 3:
+//   plane ip+1 -> window;  F_1, F_2, L_1, L_2 of plane ip (+ this lane's face column) -> registers / scratch;  __syncwarp;
+//   update plane ip -> staging;  __syncwarp;  drain;  request the next plane of the stream.
+template <class C, int PH>
+__device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather<typename C::T>& gather, int ip,
+                                               const PairLane<C>& ln, PairWindow<C>& w, typename C::T& lam_local,
+                                               typename C::T& warp_lam) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  using Upd = typename C::Upd;
+  constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, PK = C::PK, S = C::S;
+  constexpr int NEW = (PH + 1) % 3, MID = PH, OLD = (PH + 2) % 3;
+  const int wb = ip & 1;
+
+  pair_load_plane<C, NEW>(ps, ln, w);
+  const T* __restrict__ qm = ps.previous_plane();        // plane ip in the ring: face columns, neighbours' Q
+
+  // ------------------------------------------------------------ plane ip: F_1, F_2, L_1, L_2
+  T fj[2][NR], lj[2], lk[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    Phys::template flux<1, T>(w.q[MID][c], w.pr[MID][c], fj[c]);
+    lj[c] = Phys::template eigen<1, T>(w.q[MID][c], w.pr[MID][c]);
+    T F[NR];
+    Phys::template flux<2, T>(w.q[MID][c], w.pr[MID][c], F);
+    lk[c] = Phys::template eigen<2, T>(w.q[MID][c], w.pr[MID][c]);
+    T* __restrict__ FkW = ps.Fk + ln.sk + c * PK;
+#pragma unroll
+    for (int v = 0; v < NR; ++v) FkW[v * SK] = F[v];
+    ps.Lk[ln.sk + c * PK] = lk[c];
+    // the row above (c = 0) / below (c = 1) belongs to another lane: it reads this row's F_1 / L_1 from the scratch
+    T* __restrict__ FjW = ps.Fj + ln.sj + c * PJ;
+#pragma unroll
+    for (int v = 0; v < NR; ++v) FjW[v * SJ] = fj[c][v];
+    ps.Lj[ln.sj + c * PJ] = lj[c];
+    lam_local = fv_max(lam_local, fv_max(w.li[MID][c], fv_max(lj[c], lk[c])));
+  }
+  // this lane's face-halo column: F_axis / L_axis of the cell one layer outside the interior (one instruction stream for
+  // both axes, see march_face_eval)
+  {
+    T q[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) q[v] = qm[ln.f_cell * NV + v];
+    const auto pr = Phys::template prims<T>(q);
+    T F[NR];
+    T L;
+    if constexpr (has_runtime_axis<Phys, T>::value) {
+      Phys::template flux_runtime<T>(q, pr, ln.f_axis, F);
+      L = Phys::template eigen_runtime<T>(q, pr, ln.f_axis);
+    } else if (ln.f_axis == 1) {
+      Phys::template flux<1, T>(q, pr, F);
+      L = Phys::template eigen<1, T>(q, pr);
+    } else {
+      Phys::template flux<2, T>(q, pr, F);
+      L = Phys::template eigen<2, T>(q, pr);
+    }
+#pragma unroll
+    for (int v = 0; v < NR; ++v) ln.f_F[v * ln.f_comp_stride] = F[v];
+    *ln.f_L = L;
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------ update plane ip
+  const T dt = ps.dt;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int cell = ln.cell + c * S;
+    const T* __restrict__ FjR = ps.Fj + ln.sj + c * PJ;
+    const T* __restrict__ FkR = ps.Fk + ln.sk + c * PK;
+    const T* __restrict__ LjR = ps.Lj + ln.sj + c * PJ;
+    const T* __restrict__ LkR = ps.Lk + ln.sk + c * PK;
+    T qc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) qc[v] = w.q[MID][c][v];
+    // "Q_copy = Q_copy - 0.5*F[+1] + 0.5*F[-1]" for axis 0, 1, 2 in order (test.cpp:60-77)
+#pragma unroll
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], w.fi[NEW][c][v], w.fi[OLD][c][v]);
+#pragma unroll
+    for (int v = 0; v < NR; ++v)
+      qc[v] = (c == 0) ? Upd::flux(qc[v], fj[1][v], FjR[v * SJ - PJ]) : Upd::flux(qc[v], FjR[v * SJ + PJ], fj[0][v]);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + 1], FkR[v * SK - 1]);
+    // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
+#pragma unroll
+    for (int v = 0; v < C::DV; ++v)
+      qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], w.li[MID][c], w.li[NEW][c],
+                               w.li[OLD][c], dt);
+    if (c == 0) {
+      const T l_minus = LjR[-PJ];
+#pragma unroll
+      for (int v = 0; v < C::DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], qm[(cell - S) * NV + v], lj[0], lj[1], l_minus, dt);
+    } else {
+      const T l_plus = LjR[PJ];
+#pragma unroll
+      for (int v = 0; v < C::DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1], l_plus, lj[0], dt);
+    }
+    {
+      const T l_plus = LkR[1], l_minus = LkR[-1];
+#pragma unroll
+      for (int v = 0; v < C::DV; ++v)
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[c], l_plus,
+                                 l_minus, dt);
+    }
+    T* dst = ps.stage + wb * C::STAGE_ELEMS + ln.st + c * (C::P * NV);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dst[v] = qc[v];
+  }
+  if (C::USE_TMA_STORE) fence_proxy_async_smem();
+  // per-patch maximum eigenvalue over interior cells of the input state: complete at the patch's last interior plane
+  if (ip == C::P) {
+    T m = lam_local;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (ps.lane == 0 && ps.lambda_patch) ps.lambda_patch[ps.patch_of(ps.pi)] = m;
+    warp_lam = fv_max(warp_lam, m);
+    lam_local = T(0);
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------ drain, request the next plane
+  ps.drain_staged_plane(gather, ip - 1, wb);
+  // plane ip of the ring was last read by the update above: its slot takes the next plane to request
+  if (ps.lane == 0 && ps.p_seq < ps.n_seq) ps.issue_next_load(gather);
+  ps.advance_plane();
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1)
+fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
+                 typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max,
+                 const FvGather<typename C::T> gather) {
+  using T = typename C::T;
+  using Bits = typename FloatBits<T>::type;
+  constexpr int P = C::P, H = C::H, S = C::S, NR = C::NR, R = C::R, NPL = C::NPL;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  unsigned char* const ws = smem + warp * C::WARP_BYTES;
+
+  PairStream<C> ps;
+  ps.q_in = q_in; ps.q_out = q_out; ps.lambda_patch = lambda_patch; ps.dt = dt;
+  ps.ring = reinterpret_cast<T*>(ws + C::OFF_RING);
+  ps.Fj = reinterpret_cast<T*>(ws + C::OFF_FJ);          // [NR][SJ]
+  ps.Fk = reinterpret_cast<T*>(ws + C::OFF_FK);          // [NR][SK]
+  ps.Lj = reinterpret_cast<T*>(ws + C::OFF_LJ);          // [SJ]
+  ps.Lk = reinterpret_cast<T*>(ws + C::OFF_LK);          // [SK]
+  ps.stage = reinterpret_cast<T*>(ws + C::OFF_STAGE);    // [2][STAGE_ELEMS]
+  ps.full = reinterpret_cast<unsigned long long*>(ws + C::OFF_BAR);   // [R]
+  ps.lane = lane;
+
+  if (lane == 0) {
+    for (int s = 0; s < R; ++s) mbar_init(&ps.full[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  ps.n_warps = (long long)gridDim.x * C::NW;
+  ps.w_index = (long long)blockIdx.x * C::NW + warp;
+  const long long my_patches = (n_patches > ps.w_index) ? (n_patches - ps.w_index + ps.n_warps - 1) / ps.n_warps : 0;
+  ps.n_seq = (int)(my_patches * NPL);
+  ps.n_my_patches = (int)my_patches;
+  ps.pi = ps.slot = 0;
+  ps.parity = 0;
+  ps.p_seq = ps.p_ip = ps.p_pi = ps.p_slot = 0;
+  if (lane == 0)
+    for (int s = 0; s < R && ps.p_seq < ps.n_seq; ++s) ps.issue_next_load(gather);
+
+  // lane -> (row pair jp, column k): a half-warp holds the pairs {0, 2} or {1, 3}
+  PairLane<C> ln;
+  {
+    const int k = lane & 7;
+    const int jp = 2 * ((lane >> 3) & 1) + (lane >> 4);
+    const int ja = 2 * jp;
+    ln.cell = (ja + H) * S + (k + H);
+    ln.sj = (ja + 1) * C::PJ + k;
+    ln.sk = ja * C::PK + (k + 1);
+    ln.st = C::stage_index(ja, k);
+    // face column f = lane -> [axis-1 low | axis-1 high | axis-2 low | axis-2 high], P columns each
+    const int f_axis = (lane / (2 * P)) ? 2 : 1;
+    const int f_side = (lane / P) & 1;
+    const int f_pos = lane % P;
+    const int edge = f_side ? H + P : H - 1;
+    ln.f_axis = f_axis;
+    ln.f_cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
+    const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos : f_pos * C::PK + (f_side ? P + 1 : 0);
+    ln.f_F = (f_axis == 1 ? ps.Fj : ps.Fk) + slot_in_scratch;
+    ln.f_L = (f_axis == 1 ? ps.Lj : ps.Lk) + slot_in_scratch;
+    ln.f_comp_stride = (f_axis == 1) ? C::SJ : C::SK;
+  }
+
+  PairWindow<C> w;
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int v = 0; v < C::NV; ++v) w.q[s][c][v] = T(0);
+#pragma unroll
+      for (int v = 0; v < NR; ++v) w.fi[s][c][v] = T(0);
+      w.li[s][c] = T(0);
+      w.pr[s][c] = {};
+    }
+  T lam_local = T(0), warp_lam = T(0);
+
+  for (; ps.pi < ps.n_my_patches; ++ps.pi) {
+    if constexpr (C::GATHER)   // CellData::dt of this patch
+      if (gather.dt != nullptr) ps.dt = gather.dt[ps.patch_of(ps.pi)];
+    pair_pre_step<C, 0>(ps, gather, ln, w);
+    pair_pre_step<C, 1>(ps, gather, ln, w);
+    int ip = 1;
+    while (true) {
+      pair_main_step<C, 1>(ps, gather, ip, ln, w, lam_local, warp_lam);
+      if (++ip > P) break;
+      pair_main_step<C, 2>(ps, gather, ip, ln, w, lam_local, warp_lam);
+      if (++ip > P) break;
+      pair_main_step<C, 0>(ps, gather, ip, ln, w, lam_local, warp_lam);
+      if (++ip > P) break;
+    }
+  }
+  if (lane == 0) {
+    if (C::USE_TMA_STORE) tma_store_wait_all();
+    if (lambda_max != nullptr && ps.n_my_patches > 0)
+      atomicMax(reinterpret_cast<Bits*>(lambda_max), FloatBits<T>::to(warp_lam));
+  }
+}
+
+template <class C>
+struct Fv3dPairLauncher {
+  static cudaError_t prepare(FvLaunchInfo* info, long long n_patches) {
+    static int cached_ctas_per_sm[64];
+    static int cached_sms[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (cached_ctas_per_sm[dev] == 0) {
+      err = cudaFuncSetAttribute(fv3d_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+      if (err != cudaSuccess) return err;
+      int per_sm = 0, sms = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fv3d_pair_kernel<C>, C::NT, C::SMEM_BYTES);
+      if (err != cudaSuccess) return err;
+      err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (err != cudaSuccess) return err;
+      if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+      cached_sms[dev] = sms;
+      cached_ctas_per_sm[dev] = per_sm;
+    }
+    const long long ctas_needed = (n_patches + C::NW - 1) / C::NW;
+    const long long resident = (long long)cached_sms[dev] * cached_ctas_per_sm[dev];
+    info->grid = (int)(ctas_needed < resident ? ctas_needed : resident);
+    info->block = C::NT;
+    info->smem_bytes = C::SMEM_BYTES;
+    info->patches_per_tile = C::NW;
+    info->ctas_per_sm = cached_ctas_per_sm[dev];
+    return cudaSuccess;
+  }
+
+  static cudaError_t launch(const void* q_in, void* q_out, long long n_patches, double dt, void* lambda_patch,
+                            void* lambda_max, cudaStream_t stream, const FvGatherRaw* gather = nullptr) {
+    using T = typename C::T;
+    if (n_patches <= 0) return cudaSuccess;
+    FvLaunchInfo info;
+    cudaError_t err = prepare(&info, n_patches);
+    if (err != cudaSuccess) return err;
+    fv3d_pair_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
+        static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), make_gather<T>(gather));
+    return cudaGetLastError();
+  }
+};
+
+}  // namespace exahype

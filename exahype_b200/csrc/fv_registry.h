@@ -8,6 +8,7 @@
 #include "../../include/exahype_cuda.h"
 #include "fv_patch_kernel.cuh"
 #include "fv3d_march_kernel.cuh"
+#include "fv3d_pair_kernel.cuh"
 #include "fv2d_march_kernel.cuh"
 
 namespace exahype {
@@ -81,6 +82,12 @@ template <class Phys, typename T, int P, int H, int NG, int R, int MINB>
 struct March3dFamily {
   template <bool DA, bool UH> using Dense = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, false>>;
   template <bool DA, bool UH> using Gather = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, true>>;
+};
+// 3-D warp-per-patch marching (8x8x8 patches): NW warps per CTA, ring of R planes per warp
+template <class Phys, typename T, int P, int H, int NW, int R>
+struct Pair3dFamily {
+  template <bool DA, bool UH> using Dense = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, false>>;
+  template <bool DA, bool UH> using Gather = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, true>>;
 };
 // 2-D row marching: WPC warps per CTA, MINB CTAs per SM, PF rows of register prefetch
 template <class Phys, typename T, int P, int H, int WPC, int MINB, int PF>

@@ -18,11 +18,28 @@ constexpr int EU = EXAHYPE_MODEL_EULER, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_D
 #define EXAHYPE_3D_R 5    // planes in each group's TMA ring
 #endif
 
+#ifndef EXAHYPE_3D_PAIR
+#define EXAHYPE_3D_PAIR 1   // 8^3 patches: warp-per-patch kernel (fv3d_pair_kernel.cuh) instead of the three-warp groups
+#endif
+#ifndef EXAHYPE_3D_NW
+#define EXAHYPE_3D_NW 8     // warps (= patches in flight) per CTA of the warp-per-patch kernel
+#endif
+#ifndef EXAHYPE_3D_PR
+#define EXAHYPE_3D_PR 3     // planes in each warp's TMA ring
+#endif
+#if EXAHYPE_3D_PAIR
+using Main8d = Pair3dFamily<E3, double, 8, 1, EXAHYPE_3D_NW, EXAHYPE_3D_PR>;
+using Main8f = Pair3dFamily<E3, float, 8, 1, EXAHYPE_3D_NW, EXAHYPE_3D_PR>;
+#else
+using Main8d = March3dFamily<E3, double, 8, 1, EXAHYPE_3D_NG, EXAHYPE_3D_R, 1>;
+using Main8f = March3dFamily<E3, float, 8, 1, 5, 5, 1>;
+#endif
+
 const std::vector<FvEntry>& entries() {
   static const std::vector<FvEntry> v = {
       //          plane marching: phys, T, P, H, NG groups, R planes, CTAs/SM | thread per cell: phys, T, dim, P, H, G, NT, CTAs/SM
-      march_entry<March3dFamily<E3, double, 8, 1, EXAHYPE_3D_NG, EXAHYPE_3D_R, 1>, CellFamily<E3, double, 3, 8, 1, 1, 512, 1>>(EU, F64, 3, 8, 1, 5, 0),
-      march_entry<March3dFamily<E3, float, 8, 1, 5, 5, 1>, CellFamily<E3, float, 3, 8, 1, 1, 512, 1>>(EU, F32, 3, 8, 1, 5, 0),
+      march_entry<Main8d, CellFamily<E3, double, 3, 8, 1, 1, 512, 1>>(EU, F64, 3, 8, 1, 5, 0),
+      march_entry<Main8f, CellFamily<E3, float, 3, 8, 1, 1, 512, 1>>(EU, F32, 3, 8, 1, 5, 0),
       march_entry<March3dFamily<E3, double, 4, 1, 6, 6, 1>, CellFamily<E3, double, 3, 4, 1, 4, 256, 2>>(EU, F64, 3, 4, 1, 5, 0),
       march_entry<March3dFamily<E3, float, 4, 1, 6, 6, 1>, CellFamily<E3, float, 3, 4, 1, 4, 256, 2>>(EU, F32, 3, 4, 1, 5, 0),
   };
