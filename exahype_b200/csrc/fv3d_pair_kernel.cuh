@@ -93,29 +93,53 @@ struct PairStream {
   T* lambda_patch;
   T *ring, *Fj, *Fk, *Lj, *Lk, *stage;
   unsigned long long* full;
-  long long w_index, n_warps;
+  long long n_warps;  // patches between two consecutive patches of this warp
   T dt;
-  int n_seq;          // planes this warp streams = patches * (P+2)
   int n_my_patches;
   int lane;
-  int pi, slot;       // consumer cursor: patch counter, ring slot (+ mbarrier phase parity) of the next plane
+  // Every cursor below is warp-uniform and advanced by all lanes, so that it can live in uniform registers; only the
+  // TMA / mbarrier instructions themselves are issued by lane 0.
+  // consumer: patch counter, patch index, output base, ring slot (+ mbarrier phase parity) of the next plane
+  int pi, slot;
+  long long patch;
+  T* out_base;
   uint32_t parity;
-  int p_seq, p_ip, p_pi, p_slot;   // producer cursor (lane 0): next plane to request
-
-  __device__ __forceinline__ long long patch_of(int i) const { return w_index + (long long)i * n_warps; }
+  // producer: the next plane to request -- plane p_ip of the patch at p_src, into ring slot p_slot; p_left planes to go
+  const T* p_src;
+  long long p_patch;
+  int p_ip, p_slot, p_left;
 
   __device__ __forceinline__ void issue_next_load(const FvGather<T>& gather) {
+    if (p_left == 0) return;
     const bool halo_plane = (p_ip == 0) || (p_ip == C::NPL - 1);
     const int skip = halo_plane ? C::HALO_PLANE_SKIP_ELEMS : 0;
     const uint32_t bytes = halo_plane ? C::HALO_PLANE_BYTES : C::PLANE_BYTES;
-    mbar_expect_tx(&full[p_slot], bytes);
-    tma_load_1d(ring + p_slot * C::PLANE_ELEMS + skip,
-                gather.template in<C::GATHER>(q_in, patch_of(p_pi), C::PATCH_ELEMS) +
-                    (long long)(p_ip + C::H - 1) * C::PLANE_ELEMS + skip,
-                bytes, &full[p_slot]);
-    ++p_seq;
-    if (++p_ip == C::NPL) { p_ip = 0; ++p_pi; }
+    if (lane == 0) {
+      mbar_expect_tx(&full[p_slot], bytes);
+      tma_load_1d(ring + p_slot * C::PLANE_ELEMS + skip, p_src + (p_ip + C::H - 1) * C::PLANE_ELEMS + skip, bytes,
+                  &full[p_slot]);
+    }
+    --p_left;
+    if (++p_ip == C::NPL) {
+      p_ip = 0;
+      p_patch += n_warps;
+      if (C::GATHER) { if (p_left > 0) p_src = gather.q_in[p_patch]; }
+      else p_src += n_warps * C::PATCH_ELEMS;
+    }
     if (++p_slot == C::R) p_slot = 0;
+  }
+  // consumer: start of the next patch of this warp (pi already advanced; first == true for the first one)
+  __device__ __forceinline__ void begin_patch(const FvGather<T>& gather, bool first) {
+    if (!first) patch += n_warps;
+    constexpr int ELEMS = C::UNHALOED ? C::OUT_PATCH_ELEMS : C::PATCH_ELEMS;
+    if (C::GATHER) {
+      out_base = gather.q_out[patch];
+      if (gather.dt != nullptr) dt = gather.dt[patch];    // CellData::dt of this patch
+    } else if (first) {
+      out_base = q_out + patch * ELEMS;
+    } else {
+      out_base += n_warps * ELEMS;
+    }
   }
   __device__ __forceinline__ const T* wait_plane() {
     mbar_wait(&full[slot], parity);
@@ -130,10 +154,9 @@ struct PairStream {
 
   // After the closing __syncwarp of a step: write out zero-based interior plane `plane` of patch pi from staging `buffer`.
   __device__ __forceinline__ void drain_staged_plane(const FvGather<T>& gather, int plane, int buffer) {
-    const long long patch = patch_of(pi);
     const T* sbuf = stage + buffer * C::STAGE_ELEMS;
     if (C::UNHALOED) {
-      T* dst = gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + (long long)plane * C::OUT_PLANE_ELEMS;
+      T* dst = out_base + plane * C::OUT_PLANE_ELEMS;
       if (C::USE_TMA_STORE) {
         if (lane == 0) {
           tma_store_1d(dst, sbuf, C::SEG_ELEMS * (uint32_t)sizeof(T));
@@ -149,7 +172,7 @@ struct PairStream {
       }
     } else {
       // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
-      T* dst = gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + (long long)(plane + C::H) * C::PLANE_ELEMS;
+      T* dst = out_base + (plane + C::H) * C::PLANE_ELEMS;
       constexpr int ROW = C::P * C::NV;
       for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
         const int row = e / ROW;
@@ -209,7 +232,7 @@ __device__ __forceinline__ void pair_pre_step(PairStream<C>& ps, const FvGather<
   // last read before the closing __syncwarp of the previous step.  W == 1: plane 0, which every lane has read once the
   // warp meets here (halo planes are never read from the ring again).
   if (W == 1) __syncwarp();
-  if (ps.lane == 0 && (W == 1 || ps.pi >= 1) && ps.p_seq < ps.n_seq) ps.issue_next_load(gather);
+  if (W == 1 || ps.pi >= 1) ps.issue_next_load(gather);
   ps.advance_plane();
 }
 
@@ -328,7 +351,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
     T m = lam_local;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fv_max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (ps.lane == 0 && ps.lambda_patch) ps.lambda_patch[ps.patch_of(ps.pi)] = m;
+    if (ps.lane == 0 && ps.lambda_patch) ps.lambda_patch[ps.patch] = m;
     warp_lam = fv_max(warp_lam, m);
     lam_local = T(0);
   }
@@ -337,7 +360,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // ------------------------------------------------------------ drain, request the next plane
   ps.drain_staged_plane(gather, ip - 1, wb);
   // plane ip of the ring was last read by the update above: its slot takes the next plane to request
-  if (ps.lane == 0 && ps.p_seq < ps.n_seq) ps.issue_next_load(gather);
+  ps.issue_next_load(gather);
   ps.advance_plane();
 }
 
@@ -351,7 +374,7 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   constexpr int P = C::P, H = C::H, S = C::S, NR = C::NR, R = C::R, NPL = C::NPL;
 
   extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // tells the compiler that it is warp-uniform
   const int lane = threadIdx.x & 31;
   unsigned char* const ws = smem + warp * C::WARP_BYTES;
 
@@ -373,15 +396,18 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   __syncwarp();
 
   ps.n_warps = (long long)gridDim.x * C::NW;
-  ps.w_index = (long long)blockIdx.x * C::NW + warp;
-  const long long my_patches = (n_patches > ps.w_index) ? (n_patches - ps.w_index + ps.n_warps - 1) / ps.n_warps : 0;
-  ps.n_seq = (int)(my_patches * NPL);
+  const long long w_index = (long long)blockIdx.x * C::NW + warp;
+  const long long my_patches = (n_patches > w_index) ? (n_patches - w_index + ps.n_warps - 1) / ps.n_warps : 0;
   ps.n_my_patches = (int)my_patches;
   ps.pi = ps.slot = 0;
   ps.parity = 0;
-  ps.p_seq = ps.p_ip = ps.p_pi = ps.p_slot = 0;
-  if (lane == 0)
-    for (int s = 0; s < R && ps.p_seq < ps.n_seq; ++s) ps.issue_next_load(gather);
+  ps.patch = ps.p_patch = w_index;
+  ps.out_base = q_out;
+  ps.p_left = (int)(my_patches * NPL);
+  ps.p_ip = ps.p_slot = 0;
+  ps.p_src = q_in;
+  if (my_patches > 0) ps.p_src = gather.template in<C::GATHER>(q_in, w_index, C::PATCH_ELEMS);
+  for (int s = 0; s < R; ++s) ps.issue_next_load(gather);
 
   // lane -> (row pair jp, column k): a half-warp holds the pairs {0, 2} or {1, 3}
   PairLane<C> ln;
@@ -421,8 +447,7 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   T lam_local = T(0), warp_lam = T(0);
 
   for (; ps.pi < ps.n_my_patches; ++ps.pi) {
-    if constexpr (C::GATHER)   // CellData::dt of this patch
-      if (gather.dt != nullptr) ps.dt = gather.dt[ps.patch_of(ps.pi)];
+    ps.begin_patch(gather, ps.pi == 0);
     pair_pre_step<C, 0>(ps, gather, ln, w);
     pair_pre_step<C, 1>(ps, gather, ln, w);
     int ip = 1;
