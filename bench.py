@@ -169,7 +169,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
@@ -255,6 +255,16 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
+    # nvidia-smi samples every 100 ms and the timed region lasts a few tens of ms: keep the device under the same load
+    # (untimed warm-up steps, at least W more) for 0.35 s right before the timed region, so that the clock samples are
+    # taken under load and the timed steps start at load clocks
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < args.warmup or time.perf_counter() - t_warm < 0.35:
+        for _ in range(25):
+            step()
+        torch.cuda.synchronize()
+        n_warm += 25
     launches0 = runtime.launch_count()
     k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

@@ -296,7 +296,22 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
     for (int v = 0; v < NR; ++v) ln.f_F[v * ln.f_comp_stride] = F[v];
     *ln.f_L = L;
   }
+  // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
+  // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
+  // behind the __syncwarp instead of at the end of the step (half a step more lead for the TMA).
+  constexpr bool EARLY = (C::DV == 1);
+  T qn_j[2], qn_k[2][2];   // [cell]: the neighbour across axis 1 outside the pair; [cell][-1 / +1] along axis 2
+  if constexpr (EARLY) {
+    qn_j[0] = qm[(ln.cell - S) * NV];
+    qn_j[1] = qm[(ln.cell + 2 * S) * NV];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      qn_k[c][0] = qm[(ln.cell + c * S - 1) * NV];
+      qn_k[c][1] = qm[(ln.cell + c * S + 1) * NV];
+    }
+  }
   __syncwarp();
+  if constexpr (EARLY) ps.issue_next_load(gather);
 
   // ------------------------------------------------------------ update plane ip
   const T dt = ps.dt;
@@ -327,19 +342,21 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
       const T l_minus = LjR[-PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], qm[(cell - S) * NV + v], lj[0], lj[1], l_minus, dt);
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], lj[0],
+                                 lj[1], l_minus, dt);
     } else {
       const T l_plus = LjR[PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1], l_plus, lj[0], dt);
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1],
+                                 l_plus, lj[0], dt);
     }
     {
       const T l_plus = LkR[1], l_minus = LkR[-1];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[c], l_plus,
-                                 l_minus, dt);
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], EARLY ? qn_k[c][1] : qm[(cell + 1) * NV + v],
+                                 EARLY ? qn_k[c][0] : qm[(cell - 1) * NV + v], lk[c], l_plus, l_minus, dt);
     }
     T* dst = ps.stage + wb * C::STAGE_ELEMS + ln.st + c * (C::P * NV);
 #pragma unroll
@@ -360,7 +377,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // ------------------------------------------------------------ drain, request the next plane
   ps.drain_staged_plane(gather, ip - 1, wb);
   // plane ip of the ring was last read by the update above: its slot takes the next plane to request
-  ps.issue_next_load(gather);
+  if constexpr (!EARLY) ps.issue_next_load(gather);
   ps.advance_plane();
 }
 
