@@ -9,8 +9,9 @@ stateless finite-volume Rusanov update of ``examples/Batched_stateless.py:25-35`
 * an update functor whose two expressions are printed from the declaration's own statements in SymPy's ``str``
   order, i.e. the evaluation order the reference's generated C++ has, and
 * an ``extern "C"`` entry that instantiates a hand-written kernel template for the declared geometry: row marching
-  (``csrc/fv2d_march_kernel.cuh``) for 2-D patches whose side divides the warp, plane marching
-  (``csrc/fv3d_march_kernel.cuh``) for 3-D patches, thread per cell (``csrc/fv_patch_kernel.cuh``) otherwise.
+  (``csrc/fv2d_march_kernel.cuh``) for 2-D patches whose side divides the warp, warp-per-patch plane marching
+  (``csrc/fv3d_pair_kernel.cuh``) for 8x8x8 patches with one halo layer, plane marching by warp groups
+  (``csrc/fv3d_march_kernel.cuh``) for the other 3-D patches, thread per cell (``csrc/fv_patch_kernel.cuh``) otherwise.
 
 ``.code`` / ``.file()`` / ``.here()`` / ``.loop()`` follow ``CodePrinter`` (reference ``CodePrinter.py:46-71``);
 ``.build()`` compiles the unit with nvcc and returns a callable bound through ctypes.
@@ -331,7 +332,8 @@ class CUDAPrinter(CodePrinter):
     dissipation  None: as the reference's printer would emit it (variable 0 only for the reference declaration,
                  CPPPrinter.py:118-126); 'all' / 'var0' to force.
     model        'euler' | 'swe': use a committed hand-written functor family for functions declared without a body.
-    template     'auto' | 'march' | 'cell': which hand-written kernel template the entry instantiates (see module doc).
+    template     'auto' | 'pair' | 'march' | 'cell': which hand-written kernel template the entry instantiates (see
+                 module doc; 'pair' is the warp-per-patch kernel for 3-D patches of side 8, halo 1).
     """
 
     def __init__(self, kernel: KernelBuilder, function_name: str = "time_step", dtype: str = "f64",
@@ -350,12 +352,21 @@ class CUDAPrinter(CodePrinter):
         self.dissipation_all = self.program.dissipation_all if dissipation is None else dissipation == "all"
         self.model = model
         k = kernel
-        if template not in ("auto", "march", "cell"):
-            raise ValueError("template must be 'auto', 'march' or 'cell'")
+        if template not in ("auto", "pair", "march", "cell"):
+            raise ValueError("template must be 'auto', 'pair', 'march' or 'cell'")
         can_march = (k.dim == 2 and k.patch_size in (8, 16, 32)) or (k.dim == 3 and k.patch_size in (4, 8))
         if template == "march" and not can_march:
             raise UnsupportedKernel("the marching templates serve 2-D patches of side 8/16/32 and 3-D patches of side 4/8")
-        self.template = "march" if (can_march and (template == "march" or (template == "auto" and k.n_real + k.n_aux <= 6))) else "cell"
+        can_pair = k.dim == 3 and k.patch_size == 8 and k.halo_size == 1
+        if template == "pair" and not can_pair:
+            raise UnsupportedKernel("the warp-per-patch template serves 3-D patches of side 8 with one halo layer")
+        small = k.n_real + k.n_aux <= 6
+        if can_pair and (template == "pair" or (template == "auto" and small)):
+            self.template = "pair"
+        elif can_march and (template == "march" or (template == "auto" and small)):
+            self.template = "march"
+        else:
+            self.template = "cell"
         elem = 8 if dtype == "f64" else 4
         G, nt, minb = pick_geometry(k.dim, k.patch_size, k.halo_size, k.n_real, k.n_aux, elem)
         self.patches_per_tile = patches_per_tile or G
@@ -466,6 +477,10 @@ class CUDAPrinter(CodePrinter):
         elif k.dim == 2:
             header = "fv2d_march_kernel.cuh"
             launcher = lambda da, uh: (f"::exahype::Fv2dMarchAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
+                                       f"{b(da)}, {b(uh)}>")
+        elif self.template == "pair":
+            header = "fv3d_pair_kernel.cuh"
+            launcher = lambda da, uh: (f"::exahype::Fv3dPairAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
                                        f"{b(da)}, {b(uh)}>")
         else:
             header = "fv3d_march_kernel.cuh"

@@ -70,8 +70,13 @@ def test_cuda_printer_recognises_the_program():
     p = CUDAPrinter(k, model="euler")
     assert "using Physics = ::exahype::EulerPhysics<3, 5, 0>;" in p.code
     assert 'extern "C"' in p.code and "int time_step(const void* q_in" in p.code
-    assert '#include "fv3d_march_kernel.cuh"' in p.code
-    assert "::exahype::Fv3dMarchAuto<Physics, Update, double, 8, 1, false, true>::launch" in p.code
+    assert '#include "fv3d_pair_kernel.cuh"' in p.code
+    assert "::exahype::Fv3dPairAuto<Physics, Update, double, 8, 1, false, true>::launch" in p.code
+    grp = CUDAPrinter(k, model="euler", template="march")
+    assert '#include "fv3d_march_kernel.cuh"' in grp.code
+    assert "::exahype::Fv3dMarchAuto<Physics, Update, double, 8, 1, false, true>::launch" in grp.code
+    assert "Fv3dMarchAuto<Physics, Update, double, 4, 1" in CUDAPrinter(
+        batched_stateless(KernelBuilder, 3, 4, 1, 5, 0), model="euler").code
     cell = CUDAPrinter(k, model="euler", template="cell")
     assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true>" in cell.code
     assert "Fv2dMarchAuto<Physics, Update, double, 16, 1, false, false>" in CUDAPrinter(
