@@ -529,14 +529,14 @@ struct Fv3dPairLauncher {
   }
 };
 
-// what a generated unit (exahype.printers.CUDAPrinter) instantiates: a multiple of four warps per CTA (registers are
-// allocated to a CTA in units of four warps) -- 8 for fp64 (up to 255 registers per thread), 12 for fp32 -- or as many
-// as fit 227 KB of shared memory; each warp's planes through a 3-deep ring
+// what a generated unit (exahype.printers.CUDAPrinter) instantiates: 8 warps per CTA (registers are allocated to a CTA in
+// units of four warps; fp64 needs up to 255 registers per thread, fp32 fits two such CTAs per SM) or the multiple of
+// four that fits 227 KB of shared memory; each warp's planes through a 3-deep ring
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 struct Fv3dPairAutoConfig {
   using One = Fv3dPairConfig<Phys, Upd, T, P, H, 1, 3, DA, UH>;
   static constexpr int BY_SMEM = (227 * 1024) / One::WARP_BYTES;
-  static constexpr int BY_REGS = sizeof(T) == 8 ? 8 : 12;
+  static constexpr int BY_REGS = 8;
   static constexpr int NW0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int NW = NW0 >= 4 ? NW0 / 4 * 4 : (NW0 < 1 ? 1 : NW0);
   using type = Fv3dPairConfig<Phys, Upd, T, P, H, NW, 3, DA, UH>;
