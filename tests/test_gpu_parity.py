@@ -207,6 +207,22 @@ def test_every_instantiation_matches_oracle_bitwise(torch, rt, oracle, shape, di
     assert lmax == float(lmax_o)
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 147, 148 * 8, 148 * 8 + 1, 3 * 148 * 8 - 5])
+@pytest.mark.parametrize("output", ["haloed", "unhaloed"])
+def test_warp_per_patch_ragged_batches(torch, rt, oracle, n, output):
+    """The 8x8x8 kernel gives every warp its own stream of patches (csrc/fv3d_pair_kernel.cuh): batches that leave
+    warps or whole CTAs without a patch, fill the resident warps exactly, or spill one patch into a second round."""
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0, output=output)
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, n, first_patch=11)
+    want = q0.copy()
+    lam_o, lmax_o = oracle.step(cfg, want, 0.02, nthreads=4)
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.02)
+    assert_bitwise(got, want if output == "haloed" else interior(upd, want), output)
+    assert_bitwise(lam, lam_o, "lambda_patch")
+    assert lmax == float(lmax_o)
+
+
 def test_fp32_error_bound_against_fp64_oracle(torch, rt, oracle):
     """Stated fp32 bound: max |q32 - q64| <= 2e-6 * max|q64| per variable on the synthetic SWE and Euler states."""
     for model, dim, P, nr, na in (("swe", 2, 32, 3, 1), ("euler", 3, 8, 5, 0), ("euler", 2, 16, 4, 0)):
