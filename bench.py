@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--dissipation", default="var0", choices=["var0", "all"])
     ap.add_argument("--reducer", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: all-reduce(max) of lambda over NVLink peer memory (one-shot kernel) or through NCCL")
+    ap.add_argument("--no-fused", action="store_true",
+                    help="N > 1: all-reduce as a separate launch instead of the patch kernel's epilogue")
     ap.add_argument("--kernel", default="auto", choices=["auto", "cell"], help="3-D: plane-marching (auto) or thread-per-cell")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -228,10 +230,16 @@ def main():
     reducer = TimestepReducer(world, rank, backend=args.reducer) if world > 1 else None
     stream = torch.cuda.current_stream()
 
+    # all-reduce in the patch kernel's own epilogue (peer-memory backend)
+    fused = reducer is not None and reducer.backend == "peer" and not args.no_fused
+
     def step():
-        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
-        if reducer is not None:
-            reducer.allreduce_max(lam_max)
+        if fused:
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
+        else:
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+            if reducer is not None:
+                reducer.allreduce_max(lam_max)
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,7 +254,10 @@ def main():
         # the collective is exact: the reduced scalar must equal torch.distributed's own MAX over the ranks' local values
         upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
         local = lam_max.clone()
-        reducer.allreduce_max(lam_max)
+        if fused:     # the same step again, reduced by its own epilogue
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
+        else:
+            reducer.allreduce_max(lam_max)
         dist.all_reduce(local, op=dist.ReduceOp.MAX)
         torch.cuda.synchronize()
         if float(local.item()) != float(lam_max.item()) or reducer.timed_out():
@@ -270,10 +281,14 @@ def main():
     t_begin.record(stream)
     for i in range(args.steps):
         k_start[i].record(stream)
-        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
-        k_stop[i].record(stream)
-        if reducer is not None:
-            reducer.allreduce_max(lam_max)
+        if fused:
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
+            k_stop[i].record(stream)
+        else:
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+            k_stop[i].record(stream)
+            if reducer is not None:
+                reducer.allreduce_max(lam_max)
     t_end.record(stream)
     barrier()
     launches = runtime.launch_count() - launches0
@@ -364,7 +379,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": desc, "patches_per_gpu": batch, "global_patches": batch * world,
                        "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)", "kernel_variant": args.kernel,
-                       "parallelism": f"patch-sharded x{world}" + (f", allreduce-max of lambda per step ({'one-shot NVLink peer-memory kernel' if reducer.backend == 'peer' else 'NCCL'})" if world > 1 else ""),
+                       "parallelism": f"patch-sharded x{world}" + (f", allreduce-max of lambda per step ({("one-shot NVLink peer-memory exchange in the patch kernel's epilogue" if fused else 'one-shot NVLink peer-memory kernel') if reducer.backend == 'peer' else 'NCCL'})" if world > 1 else ""),
                        "l2": "inputs larger than L2: %.2f GB read + %.2f GB written per step per GPU"
                              % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
                        "kernel": info},

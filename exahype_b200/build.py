@@ -21,7 +21,7 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexahype_cuda.so")
 
 SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "synthetic.cu", "peer_reduce.cu"]
-HEADERS = ["fv_patch_kernel.cuh", "fv3d_march_kernel.cuh", "fv3d_pair_kernel.cuh", "fv2d_march_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
+HEADERS = ["fv_patch_kernel.cuh", "peer_mail.cuh", "fv3d_march_kernel.cuh", "fv3d_pair_kernel.cuh", "fv2d_march_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-lineinfo",
               "-gencode", "arch=compute_100a,code=sm_100a",

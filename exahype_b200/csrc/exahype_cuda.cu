@@ -25,6 +25,7 @@ cudaError_t peer_reducer_create(PeerReducer** out, int world, int rank);
 cudaError_t peer_reducer_local_handle(PeerReducer* r, void* out64);
 cudaError_t peer_reducer_connect(PeerReducer* r, const void* all_handles);
 cudaError_t peer_reducer_allreduce_max(PeerReducer* r, void* value, int dtype, cudaStream_t stream);
+cudaError_t peer_reducer_next_fused(PeerReducer* r, FvPeerFuse* out);
 cudaError_t peer_reducer_error(PeerReducer* r, int* flag);
 void peer_reducer_destroy(PeerReducer* r);
 cudaError_t fill_synthetic(const exahype_fv_config* cfg, void* q, long long first_cell, long long n_cells,
@@ -196,6 +197,43 @@ int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q
   return EXAHYPE_OK;
 }
 
+int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, const void* q_in, void* q_out,
+                                   int64_t n_patches, double dt, void* lambda_patch, void* lambda_max, void* stream) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  if (!reducer || !lambda_max) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "reducer / lambda_max must not be null");
+  const int var = variant_of(cfg->flags);
+  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  exahype::FvLaunchInfo info;
+  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches > 0 ? n_patches : 1);
+  if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_allreduce (launch info)");
+  exahype::PeerReducer* r = static_cast<exahype::PeerReducer*>(reducer);
+  if (!info.fused_allreduce || n_patches <= 0) {
+    // kernels without the fused epilogue (and empty shards): the step, then the stand-alone one-shot kernel
+    rc = exahype_cuda_fv_step(cfg, q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
+    if (rc) return rc;
+    return exahype_cuda_peer_reducer_allreduce_max(reducer, lambda_max, cfg->dtype, stream);
+  }
+  if (!q_in || !q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must not be null");
+  if ((reinterpret_cast<uintptr_t>(q_in) & 15) || (reinterpret_cast<uintptr_t>(q_out) & 15))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must be 16-byte aligned (TMA bulk copies)");
+  if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!(cfg->flags & EXAHYPE_FLAG_LAMBDA_ACCUMULATE)) {
+    err = cudaMemsetAsync(lambda_max, 0, elem_size(cfg->dtype), s);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaMemsetAsync(lambda_max)");
+  }
+  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}};
+  err = exahype::peer_reducer_next_fused(r, &g.peer);
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer not connected (or more than 32 ranks)");
+  err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, &g);
+  if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (fused all-reduce)");
+  g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
+
 int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_cell_data* cells, double dt,
                                    void* lambda_max, void* stream) {
   const exahype::FvEntry* e = nullptr;
@@ -210,7 +248,7 @@ int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_c
   }
   if (cells->n_patches == 0) return EXAHYPE_OK;
   if (!cells->q_in || !cells->q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cells->q_in / cells->q_out must not be null");
-  const exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt};
+  const exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt, {}};
   const int var = variant_of(cfg->flags);   // the CellData form exists for the shape's default kernel
   cudaError_t err = e->gather_launch[var](nullptr, nullptr, cells->n_patches, dt, cells->max_eigenvalue, lambda_max, s, &g);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (cell data)");

@@ -482,6 +482,9 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
     if (lambda_max != nullptr && ps.n_my_patches > 0)
       atomicMax(reinterpret_cast<Bits*>(lambda_max), FloatBits<T>::to(warp_lam));
   }
+  // multi-GPU: the global admissible-time-step scalar in the same launch -- the last warp of the grid to get here
+  // exchanges this device's maximum with every peer over NVLink (peer_mail.cuh) and leaves the result in *lambda_max
+  if (gather.peer.world > 1) fused_allreduce_max<T, Bits>(gather.peer, lambda_max, lane, gridDim.x * (unsigned)C::NW);
 }
 
 template <class C>
@@ -512,6 +515,7 @@ struct Fv3dPairLauncher {
     info->smem_bytes = C::SMEM_BYTES;
     info->patches_per_tile = C::NW;
     info->ctas_per_sm = cached_ctas_per_sm[dev];
+    info->fused_allreduce = 1;
     return cudaSuccess;
   }
 

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "peer_mail.cuh"
 #include "physics.cuh"
 
 namespace exahype {
@@ -55,6 +56,9 @@ struct FvGather {
   const T* const* q_in = nullptr;
   T* const* q_out = nullptr;
   const T* dt = nullptr;
+  // multi-GPU: the all-reduce(max) of lambda_max run by the kernel's own epilogue (kernels whose launch info says
+  // fused_allreduce; world <= 1: none).  Rides along here because this struct already reaches every kernel.
+  FvPeerFuse peer;
   template <bool GATHER>
   __device__ __forceinline__ const T* in(const T* base, long long patch, int patch_elems) const {
     if constexpr (GATHER) return q_in[patch];
@@ -75,6 +79,7 @@ struct FvGatherRaw {   // type-erased form crossing the registry's function poin
   const void* const* q_in;
   void* const* q_out;
   const void* dt;
+  FvPeerFuse peer;
 };
 template <typename T>
 inline FvGather<T> make_gather(const FvGatherRaw* raw) {
@@ -83,6 +88,7 @@ inline FvGather<T> make_gather(const FvGatherRaw* raw) {
     g.q_in = reinterpret_cast<const T* const*>(raw->q_in);
     g.q_out = reinterpret_cast<T* const*>(raw->q_out);
     g.dt = static_cast<const T*>(raw->dt);
+    g.peer = raw->peer;
   }
   return g;
 }
@@ -501,6 +507,7 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
 // host side: geometry + launch of one instantiation
 struct FvLaunchInfo {
   int grid, block, smem_bytes, patches_per_tile, ctas_per_sm;
+  int fused_allreduce = 0;   // 1: the kernel runs FvGather::peer's all-reduce(max) in its epilogue
 };
 
 template <class C>

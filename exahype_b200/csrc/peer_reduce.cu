@@ -11,6 +11,7 @@
 // a peer only does after it has consumed step s.  max is exact, so the result is bitwise the one NCCL gives.
 // A rank that never shows up trips a clock-based timeout that raises an error flag instead of hanging the GPU.
 #include "../../include/exahype_cuda.h"
+#include "peer_mail.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,66 +21,27 @@
 
 namespace exahype {
 
-struct PeerMail {
-  unsigned long long bits;   // the value (double or float bits)
-  unsigned long long seq;    // step number the value belongs to (0 = never written)
-};
-
 struct PeerReducer {
   int world = 0, rank = 0, device = 0;
   PeerMail* mine = nullptr;                 // [2][world], this rank's mailbox (cudaMalloc, IPC-exported)
   std::vector<PeerMail*> peers;             // peer r's mailbox as mapped here (peers[rank] == mine)
   PeerMail** d_peers = nullptr;             // device copy of `peers`
   int* d_error = nullptr;                   // set to 1 by a timed-out wait
+  unsigned int* d_ticket = nullptr;         // arrival counter of patch kernels that run the exchange in their epilogue
   unsigned long long seq = 0;
   bool connected = false;
 };
 
 namespace {
 
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <typename T> struct Bits;
-template <> struct Bits<double> {
-  static __device__ unsigned long long to(double x) { return (unsigned long long)__double_as_longlong(x); }
-  static __device__ double from(unsigned long long b) { return __longlong_as_double((long long)b); }
-};
-template <> struct Bits<float> {
-  static __device__ unsigned long long to(float x) { return __float_as_uint(x); }
-  static __device__ float from(unsigned long long b) { return __uint_as_float((unsigned)b); }
-};
-
 template <typename T>
 __global__ void peer_allreduce_max_kernel(T* value, PeerMail* const* peers, PeerMail* mine, int world, int rank,
                                           unsigned long long seq, long long timeout_cycles, int* error) {
   __shared__ T partial[32];
   const int t = threadIdx.x;
-  const int slot = (int)(seq & 1ull) * world;
   T v = *value;
   T got = v;
-  if (t < world) {
-    PeerMail* dst = peers[t] + slot + rank;
-    st_relaxed_sys(&dst->bits, Bits<T>::to(v));
-    st_release_sys(&dst->seq, seq);                     // the value is visible before its sequence number
-    const PeerMail* src = mine + slot + t;
-    const long long t0 = clock64();
-    bool ok = true;
-    while (ld_acquire_sys(&src->seq) != seq) {
-      if (clock64() - t0 > timeout_cycles) { ok = false; break; }
-    }
-    if (ok) got = Bits<T>::from(ld_acquire_sys(&src->bits));
-    else atomicExch(error, 1);
-  }
+  if (t < world) got = peer_exchange_with<T>(peers, mine, world, rank, t, seq, timeout_cycles, error, v);
   // max over the block (world <= 1024 threads): std::max semantics, NaN-free inputs
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -106,6 +68,8 @@ cudaError_t peer_reducer_create(PeerReducer** out, int world, int rank) {
   if (err == cudaSuccess) err = cudaMalloc(&r->d_peers, sizeof(PeerMail*) * world);
   if (err == cudaSuccess) err = cudaMalloc(&r->d_error, sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(r->d_error, 0, sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc(&r->d_ticket, sizeof(unsigned int));
+  if (err == cudaSuccess) err = cudaMemset(r->d_ticket, 0, sizeof(unsigned int));
   if (err != cudaSuccess) { delete r; return err; }
   r->peers.assign(world, nullptr);
   r->peers[rank] = r->mine;
@@ -151,6 +115,21 @@ cudaError_t peer_reducer_allreduce_max(PeerReducer* r, void* value, int dtype, c
   return cudaGetLastError();
 }
 
+// the arguments of the NEXT exchange, for a patch kernel that runs it in its epilogue (counts as one allreduce_max call)
+cudaError_t peer_reducer_next_fused(PeerReducer* r, FvPeerFuse* out) {
+  if (!r->connected) return cudaErrorNotReady;
+  if (r->world > 32) return cudaErrorNotSupported;      // one lane per peer
+  out->peers = r->d_peers;
+  out->mine = r->mine;
+  out->ticket = r->d_ticket;
+  out->error = r->d_error;
+  out->seq = ++r->seq;
+  out->timeout_cycles = 20000000000ll;
+  out->world = r->world;
+  out->rank = r->rank;
+  return cudaSuccess;
+}
+
 cudaError_t peer_reducer_error(PeerReducer* r, int* flag) {
   return cudaMemcpy(flag, r->d_error, sizeof(int), cudaMemcpyDeviceToHost);
 }
@@ -162,6 +141,7 @@ void peer_reducer_destroy(PeerReducer* r) {
   if (r->mine) cudaFree(r->mine);
   if (r->d_peers) cudaFree(r->d_peers);
   if (r->d_error) cudaFree(r->d_error);
+  if (r->d_ticket) cudaFree(r->d_ticket);
   delete r;
 }
 

@@ -149,6 +149,12 @@ class TimestepReducer:
             dist.all_reduce(value, op=dist.ReduceOp.MAX)
         return value
 
+    @property
+    def peer_handle(self):
+        """The library's peer-memory reducer (None unless ``backend == 'peer'``): what ``PatchUpdate.step(reducer=...)``
+        hands to ``exahype_cuda_fv_step_allreduce`` for the all-reduce in the patch kernel's own epilogue."""
+        return self._peer if self._peer else None
+
     def timed_out(self) -> bool:
         """True if a peer-memory wait gave up (a rank never arrived).  Synchronises the device."""
         if not self._peer:

@@ -71,6 +71,7 @@ def load(path: Optional[str] = None) -> ctypes.CDLL:
     lib.exahype_cuda_fv_supported.argtypes = [c_cfg]
     lib.exahype_cuda_fv_list.argtypes = [c_cfg, i32]
     lib.exahype_cuda_fv_step.argtypes = [c_cfg, vp, vp, i64, dbl, vp, vp, vp]
+    lib.exahype_cuda_fv_step_allreduce.argtypes = [c_cfg, vp, vp, vp, i64, dbl, vp, vp, vp]
     lib.exahype_cuda_fv_step_cell_data.argtypes = [c_cfg, ctypes.POINTER(CellData), dbl, vp, vp]
     lib.exahype_cuda_time_step_host.argtypes = [c_cfg, vp, vp, i64, dbl, vp, vp]
     lib.exahype_cuda_host_pipeline_configure.argtypes = [i64, i32]
@@ -220,11 +221,15 @@ class PatchUpdate:
         return numel // per
 
     def step(self, q_in, q_out=None, dt: float = 0.0, lambda_patch=None, lambda_max=None, stream=None,
-             accumulate_lambda: bool = False):
+             accumulate_lambda: bool = False, reducer=None):
         """Asynchronous update of a batch on the current CUDA device.
 
         ``q_in``/``q_out``/``lambda_*`` are contiguous CUDA tensors of this object's dtype.  ``q_out=None`` means in
         place (haloed output only).  Returns ``q_out``.
+
+        ``reducer`` (multi-GPU): a :class:`exahype_b200.dist.TimestepReducer` with the peer-memory backend -- the
+        all-reduce(max) of ``lambda_max`` over the ranks then runs in the same launch where the kernel supports it
+        (``exahype_cuda_fv_step_allreduce``); with any other reducer it is ``step`` followed by ``allreduce_max``.
         """
         import torch
         tdt = torch.float64 if self.dtype == "f64" else torch.float32
@@ -247,11 +252,22 @@ class PatchUpdate:
         if stream is None:
             stream = torch.cuda.current_stream(q_in.device).cuda_stream
         c = self.config(accumulate_lambda)
+        fused = reducer is not None and getattr(reducer, "peer_handle", None)
+        if reducer is not None and lambda_max is None:
+            raise ValueError("a reducer needs lambda_max")
         with torch.cuda.device(q_in.device):
-            check(self._lib.exahype_cuda_fv_step(
-                ctypes.byref(c), q_in.data_ptr(), q_out.data_ptr(), n, float(dt),
-                lambda_patch.data_ptr() if lambda_patch is not None else None,
-                lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
+            if fused:
+                check(self._lib.exahype_cuda_fv_step_allreduce(
+                    ctypes.byref(c), reducer.peer_handle, q_in.data_ptr(), q_out.data_ptr(), n, float(dt),
+                    lambda_patch.data_ptr() if lambda_patch is not None else None, lambda_max.data_ptr(), stream),
+                    self._lib)
+            else:
+                check(self._lib.exahype_cuda_fv_step(
+                    ctypes.byref(c), q_in.data_ptr(), q_out.data_ptr(), n, float(dt),
+                    lambda_patch.data_ptr() if lambda_patch is not None else None,
+                    lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
+        if reducer is not None and not fused:
+            reducer.allreduce_max(lambda_max, stream=stream)
         return q_out
 
     def step_cell_data(self, q_in_ptrs, q_out_ptrs, dt=0.0, dt_patch=None, max_eigenvalue=None, lambda_max=None,

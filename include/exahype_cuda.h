@@ -185,6 +185,16 @@ int exahype_cuda_peer_reducer_local_handle(void* reducer, void* handle64);
 int exahype_cuda_peer_reducer_connect(void* reducer, const void* all_handles);
 int exahype_cuda_peer_reducer_allreduce_max(void* reducer, void* value, int dtype, void* stream);
 int exahype_cuda_peer_reducer_status(void* reducer, int* flag);
+/*
+ * exahype_cuda_fv_step followed by exahype_cuda_peer_reducer_allreduce_max(lambda_max), as ONE launch where the shape's
+ * kernel supports it (the warp-per-patch kernel of 8x8x8 patches): the last warp of the grid to finish exchanges the
+ * device's maximum with every peer from the kernel's own epilogue, so no second kernel sits between two steps.  Other
+ * shapes (and empty shards) fall back to the two launches.  Same arguments and flags as exahype_cuda_fv_step;
+ * lambda_max is required and holds the maximum over ALL ranks afterwards.  Collective: counts as one allreduce_max call.
+ * The reference has no counterpart (its kernel is serial).
+ */
+int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, const void* q_in, void* q_out,
+                                   int64_t n_patches, double dt, void* lambda_patch, void* lambda_max, void* stream);
 int exahype_cuda_peer_reducer_destroy(void* reducer);
 
 #ifdef __cplusplus
