@@ -29,15 +29,15 @@ __device__ __forceinline__ void tma_store_wait_read_all_but_one() {
 }
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int NW_, int R_, bool DISS_ALL_, bool UNHALOED_,
-          bool GATHER_ = false>
+          bool GATHER_ = false, int SB_ = 2>
 struct Fv3dPairConfig {
   using Phys = Phys_;
   using Upd = Upd_;
   using T = T_;
-  static constexpr int DIM = 3, P = P_, H = H_, NW = NW_, R = R_;
+  static constexpr int DIM = 3, P = P_, H = H_, NW = NW_, R = R_, SB = SB_;   // SB: output staging buffers per warp
   static constexpr bool DISS_ALL = DISS_ALL_, UNHALOED = UNHALOED_, GATHER = GATHER_;
   static_assert(P == 8 && H == 1, "one warp per 8x8 plane: 32 row pairs and 32 face-halo columns");
-  static_assert(NW >= 1 && NW <= 32 && R >= 3, "pair-march geometry");
+  static_assert(NW >= 1 && NW <= 32 && R >= 3 && (SB == 1 || SB == 2), "pair-march geometry");
 
   static constexpr int NR = Phys::NR, NA = Phys::NA, NV = NR + NA;
   static constexpr int S = P + 2 * H;
@@ -74,7 +74,7 @@ struct Fv3dPairConfig {
   static constexpr int OFF_LJ = align_up(OFF_FK + NR * SK * (int)sizeof(T), 16);
   static constexpr int OFF_LK = align_up(OFF_LJ + SJ * (int)sizeof(T), 16);
   static constexpr int OFF_STAGE = align_up(OFF_LK + SK * (int)sizeof(T), 128);
-  static constexpr int OFF_BAR = align_up(OFF_STAGE + 2 * STAGE_ELEMS * (int)sizeof(T), 16);
+  static constexpr int OFF_BAR = align_up(OFF_STAGE + SB * STAGE_ELEMS * (int)sizeof(T), 16);
   static constexpr int WARP_BYTES = align_up(OFF_BAR + R * 8, 128);
   static constexpr int SMEM_BYTES = NW * WARP_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "warps do not fit the 227 KB of shared memory per CTA");
@@ -162,7 +162,7 @@ struct PairStream {
           tma_store_1d(dst, sbuf, C::SEG_ELEMS * (uint32_t)sizeof(T));
           tma_store_1d(dst + C::SEG_ELEMS, sbuf + C::SEG_PITCH, C::SEG_ELEMS * (uint32_t)sizeof(T));
           tma_store_commit();
-          tma_store_wait_read_all_but_one();    // the other staging buffer (written next step) is free again
+          if (C::SB == 2) tma_store_wait_read_all_but_one();    // the other staging buffer (written next step) is free again
         }
       } else {
         for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
@@ -248,7 +248,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   using Upd = typename C::Upd;
   constexpr int NV = C::NV, NR = C::NR, SJ = C::SJ, SK = C::SK, PJ = C::PJ, PK = C::PK, S = C::S;
   constexpr int NEW = (PH + 1) % 3, MID = PH, OLD = (PH + 2) % 3;
-  const int wb = ip & 1;
+  const int wb = (C::SB == 2) ? (ip & 1) : 0;
 
   pair_load_plane<C, NEW>(ps, ln, w);
   const T* __restrict__ qm = ps.previous_plane();        // plane ip in the ring: face columns, neighbours' Q
@@ -310,6 +310,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
       qn_k[c][1] = qm[(ln.cell + c * S + 1) * NV];
     }
   }
+  if (C::SB == 1 && C::USE_TMA_STORE && ps.lane == 0) tma_store_wait_read();   // the one staging buffer is free again
   __syncwarp();
   if constexpr (EARLY) ps.issue_next_load(gather);
 
@@ -534,16 +535,18 @@ struct Fv3dPairLauncher {
 };
 
 // what a generated unit (exahype.printers.CUDAPrinter) instantiates: 8 warps per CTA (registers are allocated to a CTA in
-// units of four warps; fp64 needs up to 255 registers per thread, fp32 fits two such CTAs per SM) or the multiple of
-// four that fits 227 KB of shared memory; each warp's planes through a 3-deep ring
+// units of four warps; fp64 needs up to 255 registers per thread, fp32 fits two such CTAs per SM) with a 4-deep ring
+// and one staging buffer per warp if that fits 227 KB of shared memory, else a 3-deep ring, else fewer warps
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 struct Fv3dPairAutoConfig {
-  using One = Fv3dPairConfig<Phys, Upd, T, P, H, 1, 3, DA, UH>;
-  static constexpr int BY_SMEM = (227 * 1024) / One::WARP_BYTES;
-  static constexpr int BY_REGS = 8;
-  static constexpr int NW0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+  using One4 = Fv3dPairConfig<Phys, Upd, T, P, H, 1, 4, DA, UH, false, 1>;
+  using One3 = Fv3dPairConfig<Phys, Upd, T, P, H, 1, 3, DA, UH, false, 1>;
+  static constexpr bool DEEP = 8 * One4::WARP_BYTES + 16 <= 227 * 1024;
+  static constexpr int R = DEEP ? 4 : 3;
+  static constexpr int BY_SMEM = (227 * 1024 - 16) / (DEEP ? One4::WARP_BYTES : One3::WARP_BYTES);
+  static constexpr int NW0 = BY_SMEM < 8 ? BY_SMEM : 8;
   static constexpr int NW = NW0 >= 4 ? NW0 / 4 * 4 : (NW0 < 1 ? 1 : NW0);
-  using type = Fv3dPairConfig<Phys, Upd, T, P, H, NW, 3, DA, UH>;
+  using type = Fv3dPairConfig<Phys, Upd, T, P, H, NW, R, DA, UH, false, 1>;
 };
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 using Fv3dPairAuto = Fv3dPairLauncher<typename Fv3dPairAutoConfig<Phys, Upd, T, P, H, DA, UH>::type>;

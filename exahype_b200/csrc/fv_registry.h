@@ -84,10 +84,10 @@ struct March3dFamily {
   template <bool DA, bool UH> using Gather = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, true>>;
 };
 // 3-D warp-per-patch marching (8x8x8 patches): NW warps per CTA, ring of R planes per warp
-template <class Phys, typename T, int P, int H, int NW, int R>
+template <class Phys, typename T, int P, int H, int NW, int R, int SB = 2>
 struct Pair3dFamily {
-  template <bool DA, bool UH> using Dense = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, false>>;
-  template <bool DA, bool UH> using Gather = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, true>>;
+  template <bool DA, bool UH> using Dense = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, false, SB>>;
+  template <bool DA, bool UH> using Gather = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, true, SB>>;
 };
 // 2-D row marching: WPC warps per CTA, MINB CTAs per SM, PF rows of register prefetch
 template <class Phys, typename T, int P, int H, int WPC, int MINB, int PF>
