@@ -331,6 +331,22 @@ def main():
         del host_in, host_out
         runtime.load().exahype_cuda_host_pipeline_release()
 
+    variants = None
+    if args.variants and world == 1:
+        variants = time_variants(torch, runtime, args)
+    # the other BASELINE configurations next to the headline one (kernel-only, a few ms each): parity-test cases, not
+    # bench lines, reported so that one run shows every committed kernel family against the same roofline
+    others = None
+    if world == 1 and not args.no_others:
+        peak_gbs, _ = measured_hbm_peak()
+        others = {}
+        for wl in ("c2", "c4", "c4f32"):
+            if wl == args.workload:
+                continue
+            r = time_kernel_only(torch, runtime, wl)
+            others[wl] = {"workload": WORKLOADS[wl][8], "kernel_ms": r["ms"], "value": r["cell_updates_per_s"],
+                          "achieved_GBs": r["algorithmic_GBs"], "frac": r["algorithmic_GBs"] / peak_gbs}
+
     # --- the same step under sustained load (informative): 1.2 s of back-to-back launches drive the board into its power
     # limit; the last third is timed, with the SM clock sampled meanwhile
     sustained = None
@@ -351,22 +367,6 @@ def main():
                      "achieved_GBs": upd.algorithmic_bytes_per_patch * batch / (sus_ms * 1e-3) / 1e9,
                      "launches": n_sus, "timed": n_sus - 2 * n_sus // 3, "clocks": s2.stop(),
                      "note": "after ~0.8 s of back-to-back launches (board at its power limit, SM clock lowered)"}
-
-    variants = None
-    if args.variants and world == 1:
-        variants = time_variants(torch, runtime, args)
-    # the other BASELINE configurations next to the headline one (kernel-only, a few ms each): parity-test cases, not
-    # bench lines, reported so that one run shows every committed kernel family against the same roofline
-    others = None
-    if world == 1 and not args.no_others:
-        peak_gbs, _ = measured_hbm_peak()
-        others = {}
-        for wl in ("c2", "c4", "c4f32"):
-            if wl == args.workload:
-                continue
-            r = time_kernel_only(torch, runtime, wl)
-            others[wl] = {"workload": WORKLOADS[wl][8], "kernel_ms": r["ms"], "value": r["cell_updates_per_s"],
-                          "achieved_GBs": r["algorithmic_GBs"], "frac": r["algorithmic_GBs"] / peak_gbs}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()

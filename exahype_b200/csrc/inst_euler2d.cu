@@ -13,6 +13,9 @@ using E2 = EulerPhysics<2, 4, 0>;
 using E2ref = EulerPhysics<2, 5, 5>;
 constexpr int EU = EXAHYPE_MODEL_EULER, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_DTYPE_F32;
 
+#ifndef EXAHYPE_2D_MINB16
+#define EXAHYPE_2D_MINB16 4   // CTAs (of four warps) per SM of the same kernel
+#endif
 #ifndef EXAHYPE_2D_PF16
 #define EXAHYPE_2D_PF16 2   // register prefetch distance (rows) of the fp64 16x16 row-marching kernel
 #endif
@@ -20,7 +23,7 @@ constexpr int EU = EXAHYPE_MODEL_EULER, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_D
 const std::vector<FvEntry>& entries() {
   static const std::vector<FvEntry> v = {
       //          row marching: phys, T, P, H, warps/CTA, CTAs/SM, PF | thread per cell: phys, T, dim, P, H, G, NT, CTAs/SM
-      march_entry<March2dFamily<E2, double, 16, 1, 4, 4, EXAHYPE_2D_PF16>, CellFamily<E2, double, 2, 16, 1, 1, 256, 2>>(EU, F64, 2, 16, 1, 4, 0),
+      march_entry<March2dFamily<E2, double, 16, 1, 4, EXAHYPE_2D_MINB16, EXAHYPE_2D_PF16>, CellFamily<E2, double, 2, 16, 1, 1, 256, 2>>(EU, F64, 2, 16, 1, 4, 0),
       march_entry<March2dFamily<E2, float, 16, 1, 4, 4, 3>, CellFamily<E2, float, 2, 16, 1, 1, 256, 2>>(EU, F32, 2, 16, 1, 4, 0),
       march_entry<March2dFamily<E2, double, 8, 1, 4, 4, 2>, CellFamily<E2, double, 2, 8, 1, 4, 256, 2>>(EU, F64, 2, 8, 1, 4, 0),
       cell_entry<CellFamily<E2, double, 2, 3, 1, 28, 256, 2>>(EU, F64, 2, 3, 1, 4, 0),
