@@ -299,7 +299,10 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
   // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
   // behind the __syncwarp instead of at the end of the step (half a step more lead for the TMA).
-  constexpr bool EARLY = (C::DV == 1);
+#ifndef EXAHYPE_3D_EARLY_HALOED
+#define EXAHYPE_3D_EARLY_HALOED 1
+#endif
+  constexpr bool EARLY = (C::DV == 1) && (C::UNHALOED || EXAHYPE_3D_EARLY_HALOED);
   T qn_j[2], qn_k[2][2];   // [cell]: the neighbour across axis 1 outside the pair; [cell][-1 / +1] along axis 2
   if constexpr (EARLY) {
     qn_j[0] = qm[(ln.cell - S) * NV];
