@@ -14,7 +14,10 @@
 //     step: nothing but the window is carried from plane to plane, the scratch is single buffered;
 //   * all synchronisation is __syncwarp (two per plane).  Warps are independent: no named barriers, no CTA barrier after
 //     start-up, every warp has its own TMA ring (1-D bulk copies + mbarrier complete_tx), scratch and output staging;
-//   * finished planes leave through a two-deep staging buffer and TMA bulk stores, as in fv3d_march_kernel.cuh.
+//   * finished planes leave through SB staging buffers (one by default: the shared memory goes to a fourth ring slot
+//     instead) and TMA bulk stores; the cursors of ring, stream and output are warp-uniform and advanced by all lanes,
+//     so that the TMA instructions take uniform-register operands instead of sitting in single-lane divergent blocks;
+//   * multi-GPU: the all-reduce(max) of lambda_max can run in this kernel's epilogue (peer_mail.cuh).
 //
 // Bank-conflict-free for fp64: a half-warp holds row pairs {0, 2} or {1, 3} (rows 0/1 and 4/5, resp. 2/3 and 6/7), the
 // AoS plane has a cell stride of 5 doubles, scratch rows are pitched 10, the staging buffer is two padded segments.
@@ -406,7 +409,7 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   ps.Fk = reinterpret_cast<T*>(ws + C::OFF_FK);          // [NR][SK]
   ps.Lj = reinterpret_cast<T*>(ws + C::OFF_LJ);          // [SJ]
   ps.Lk = reinterpret_cast<T*>(ws + C::OFF_LK);          // [SK]
-  ps.stage = reinterpret_cast<T*>(ws + C::OFF_STAGE);    // [2][STAGE_ELEMS]
+  ps.stage = reinterpret_cast<T*>(ws + C::OFF_STAGE);    // [SB][STAGE_ELEMS]
   ps.full = reinterpret_cast<unsigned long long*>(ws + C::OFF_BAR);   // [R]
   ps.lane = lane;
 
