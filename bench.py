@@ -103,6 +103,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU arm
+def host_threads() -> int:
+    """All the host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would time the CPU arm on one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(workload: str, min_seconds: float, sample_patches: int):
     """Times the CPU oracle (contraction-free -O3 build, OpenMP over patches: all host threads) on a bounded sample of
     the workload.  Returns (cell-updates/s, description dict)."""
@@ -111,7 +120,7 @@ def cpu_reference_rate(workload: str, min_seconds: float, sample_patches: int):
     model, dim, P, h, nr, na, dtype, _, _ = WORKLOADS[workload]
     cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
                          model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
-    threads = O.max_threads()
+    threads = host_threads()
     npdt = np.float64 if dtype == "f64" else np.float32
     q0 = O.fill_synthetic(cfg, sample_patches, dtype=npdt)
     q = q0.copy()
@@ -140,7 +149,7 @@ def run_reference_arm(args):
     import oracle as O
     cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
                          model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
-    threads = O.max_threads()
+    threads = host_threads()
     sample = min(batch, args.cpu_sample)
     npdt = np.float64 if dtype == "f64" else np.float32
     q0 = O.fill_synthetic(cfg, sample, dtype=npdt)
@@ -400,7 +409,7 @@ def main():
             line["sustained"] = sustained
         if variants is not None:
             line["variants"] = variants
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:      # the CPU baseline belongs to the N = 1 line (bench contract)
             cpu_value, cpu_desc = cpu_reference_rate(args.workload, args.cpu_seconds, min(batch, args.cpu_sample))
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, **cpu_desc}
         print(json.dumps(line), flush=True)
