@@ -374,6 +374,7 @@ def main():
         sus_ms = a.elapsed_time(b) / (n_sus - 2 * n_sus // 3)
         sustained = {"ms_per_step": sus_ms, "value": cells_per_step / (sus_ms * 1e-3), "unit": UNIT,
                      "achieved_GBs": upd.algorithmic_bytes_per_patch * batch / (sus_ms * 1e-3) / 1e9,
+                     "frac_of_burst_peak": upd.algorithmic_bytes_per_patch * batch / (sus_ms * 1e-3) / 1e9 / measured_hbm_peak()[0],
                      "launches": n_sus, "timed": n_sus - 2 * n_sus // 3, "clocks": s2.stop(),
                      "note": "after ~0.8 s of back-to-back launches (board at its power limit, SM clock lowered)"}
 
