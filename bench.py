@@ -275,7 +275,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)
+        time.sleep(0.5)      # nvidia-smi needs a few hundred ms before its first sample
     # the sampler's start-up left the device idle for a moment: W more untimed steps right before the timed region.
     # Kept SHORT on purpose: this is a burst measurement like MEASURED_PEAKS.json's copy peak (best of 10) -- after
     # ~35 ms of back-to-back launches the board reaches its 1000 W power limit and lowers the SM clock
