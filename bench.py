@@ -174,6 +174,41 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, device_index: int):
+    """Best effort: run this process on the cores of the NUMA node its GPU hangs off, so that the pinned host buffers of
+    the e2e leg (first touch) are local to the PCIe root the copies go through.  Returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id          # e.g. 0000:1B:00.0 (torch >= 2.3)
+    except Exception:
+        try:
+            import ctypes
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, device_index) != 0:
+                return None
+            bus = buf.value.decode()
+        except Exception:
+            return None
+    try:
+        if isinstance(bus, int):
+            return None
+        path = f"/sys/bus/pci/devices/{bus.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -195,6 +230,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="e2e leg: do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-sustained", action="store_true", help="skip the sustained-load (power-limited) leg")
     ap.add_argument("--no-others", action="store_true", help="skip the kernel-only timings of the other BASELINE workloads")
     ap.add_argument("--variants", action="store_true", help="also time the other output/dissipation variants and workloads")
@@ -316,6 +352,8 @@ def main():
     # --- end to end through the host-facing C-ABI call (pinned host buffers, copies inside the timed region)
     e2e = None
     if not args.no_e2e:
+        affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        numa_node = None if args.no_numa_bind else bind_to_gpu_numa_node(torch, local_rank)
         host_in = torch.empty(upd.in_shape(batch), dtype=tdt).pin_memory()
         host_in.copy_(q_in)
         host_out = torch.empty(upd.out_shape(batch), dtype=tdt).pin_memory()
@@ -336,9 +374,12 @@ def main():
                "d2h_bytes_per_step": int(host_out.numel() * es + es) * world,
                "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
                "api": "exahype_cuda_time_step_host (chunked H2D -> kernel -> D2H over 3 stream slots)",
-               "lambda_max_matches_device": bool(float(lam_e2e) == float(lam_patch.max().item()))}
+               "lambda_max_matches_device": bool(float(lam_e2e) == float(lam_patch.max().item())),
+               "host_numa_node": numa_node}
         del host_in, host_out
         runtime.load().exahype_cuda_host_pipeline_release()
+        if numa_node is not None and affinity:
+            os.sched_setaffinity(0, affinity)      # the CPU baseline below uses every core again
 
     variants = None
     if args.variants and world == 1:
