@@ -62,8 +62,15 @@ struct Fv2dMarchConfig {
 #ifndef EXAHYPE_2D_L2_BYTES
 #define EXAHYPE_2D_L2_BYTES 2048
 #endif
+  // Small patches (all their rows within EXAHYPE_2D_L2_WHOLE bytes: 16x16 fp64 is 10 KB) are requested whole by one
+  // prefetch before the march: no per-row prefetch instructions at all (C2 0.2152 -> 0.2136 ms); the eviction argument
+  // above concerns the 37 KB patches, which keep the short window.
+#ifndef EXAHYPE_2D_L2_WHOLE
+#define EXAHYPE_2D_L2_WHOLE 12288
+#endif
   static constexpr bool L2_BULK = EXAHYPE_2D_L2 && (ROW_BYTES % 16 == 0);
-  static constexpr int L2_ROWS_WANTED = PF + 1 + (EXAHYPE_2D_L2_BYTES + ROW_BYTES - 1) / ROW_BYTES;
+  static constexpr int L2_ROWS_WANTED = (NROW * ROW_BYTES <= EXAHYPE_2D_L2_WHOLE)
+                                            ? NROW : PF + 1 + (EXAHYPE_2D_L2_BYTES + ROW_BYTES - 1) / ROW_BYTES;
   static constexpr int L2_ROWS = L2_ROWS_WANTED < NROW ? L2_ROWS_WANTED : NROW;
   static_assert(VEC == 32 || VEC == 16 || VEC == (int)sizeof(T), "vector width of the global accesses");
   static_assert(VEC == (int)sizeof(T) || CELL_BYTES % VEC == 0, "a cell must be a whole number of vectors");
