@@ -159,3 +159,18 @@ template <class T> __device__ T maxEigenvalue(const T* Q, int normal) {
     assert src.read_text().startswith('#include "Functions.cuh"')
     built = printer.build(directory=str(tmp_path), include_dirs=[str(tmp_path)])
     assert os.path.exists(built.lib_path)
+
+
+def test_generated_3d_unit_instantiates_the_warp_per_patch_template(tmp_path):
+    """8x8x8 patches: `template='auto'` picks csrc/fv3d_pair_kernel.cuh (Fv3dPairAuto) and the unit cross-compiles for
+    sm_100a, fp64 and fp32, exporting the drop-in entry."""
+    import ctypes
+    k = batched_stateless(KernelBuilder, 3, 8, 1, 5, 0)
+    for dtype in ("f64", "f32"):
+        p = CUDAPrinter(k, model="euler", dtype=dtype, function_name=f"step3d_{dtype}")
+        assert p.template == "pair" and "Fv3dPairAuto<Physics, Update" in p.code
+        built = p.build(directory=str(tmp_path))
+        assert os.path.exists(built.lib_path)
+        assert hasattr(ctypes.CDLL(built.lib_path), f"step3d_{dtype}")
+    with pytest.raises(Exception):
+        CUDAPrinter(batched_stateless(KernelBuilder, 3, 4, 1, 5, 0), model="euler", template="pair")
