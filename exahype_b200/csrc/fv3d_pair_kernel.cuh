@@ -27,6 +27,11 @@
 
 namespace exahype {
 
+template <class Upd, typename T, class = void>
+struct has_dissipation_m : std::false_type {};
+template <class Upd, typename T>
+struct has_dissipation_m<Upd, T, std::void_t<decltype(&Upd::template dissipation_m<T>)>> : std::true_type {};
+
 __device__ __forceinline__ void tma_store_wait_read_all_but_one() {
   asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
@@ -206,6 +211,7 @@ struct PairWindow {
   T fi[3][2][C::NR];
   T li[3][2];
   Prims pr[3][2];
+  T m0[2];     // max(L_0 of the current plane, L_0 of the one before it): computed as the previous plane's "plus" maximum
 };
 
 // plane `W` of the window <- the plane the stream delivers next: state, primitives, F_0, L_0
@@ -234,7 +240,11 @@ __device__ __forceinline__ void pair_pre_step(PairStream<C>& ps, const FvGather<
   // The slot requested next is that of the previous plane of the stream.  W == 0: the last plane of the previous patch,
   // last read before the closing __syncwarp of the previous step.  W == 1: plane 0, which every lane has read once the
   // warp meets here (halo planes are never read from the ring again).
-  if (W == 1) __syncwarp();
+  if (W == 1) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) w.m0[c] = fv_max(w.li[1][c], w.li[0][c]);
+    __syncwarp();
+  }
   if (W == 1 || ps.pi >= 1) ps.issue_next_load(gather);
   ps.advance_plane();
 }
@@ -322,6 +332,9 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
 
   // ------------------------------------------------------------ update plane ip
   const T dt = ps.dt;
+  constexpr bool SHARE_MAX = has_dissipation_m<Upd, T>::value;
+  T mj = T(0);
+  if constexpr (SHARE_MAX) mj = fv_max(lj[1], lj[0]);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int cell = ln.cell + c * S;
@@ -341,22 +354,45 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
 #pragma unroll
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + 1], FkR[v * SK - 1]);
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
-#pragma unroll
-    for (int v = 0; v < C::DV; ++v)
-      qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], w.li[MID][c], w.li[NEW][c],
-                               w.li[OLD][c], dt);
-    if (c == 0) {
-      const T l_minus = LjR[-PJ];
+    if constexpr (SHARE_MAX) {
+      // max(L, L') of a pair of cells serves both: along axis 0 it is carried from the previous step (m0), inside the
+      // lane's row pair it is mj
+      const T m_up = fv_max(w.li[NEW][c], w.li[MID][c]);
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], lj[0],
-                                 lj[1], l_minus, dt);
+        qc[v] = Upd::dissipation_m(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], m_up, w.m0[c], dt);
+      w.m0[c] = m_up;
+      if (c == 0) {
+        const T m_minus = fv_max(LjR[-PJ], lj[0]);
+#pragma unroll
+        for (int v = 0; v < C::DV; ++v)
+          qc[v] = Upd::dissipation_m(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], mj,
+                                     m_minus, dt);
+      } else {
+        const T m_plus = fv_max(LjR[PJ], lj[1]);
+#pragma unroll
+        for (int v = 0; v < C::DV; ++v)
+          qc[v] = Upd::dissipation_m(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v],
+                                     m_plus, mj, dt);
+      }
     } else {
-      const T l_plus = LjR[PJ];
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1],
-                                 l_plus, lj[0], dt);
+        qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], w.li[MID][c], w.li[NEW][c],
+                                 w.li[OLD][c], dt);
+      if (c == 0) {
+        const T l_minus = LjR[-PJ];
+#pragma unroll
+        for (int v = 0; v < C::DV; ++v)
+          qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], lj[0],
+                                   lj[1], l_minus, dt);
+      } else {
+        const T l_plus = LjR[PJ];
+#pragma unroll
+        for (int v = 0; v < C::DV; ++v)
+          qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1],
+                                   l_plus, lj[0], dt);
+      }
     }
     {
       const T l_plus = LkR[1], l_minus = LkR[-1];
