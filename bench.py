@@ -225,6 +225,11 @@ def main():
     ap.add_argument("--no-fused", action="store_true",
                     help="N > 1: all-reduce as a separate launch instead of the patch kernel's epilogue")
     ap.add_argument("--kernel", default="auto", choices=["auto", "cell"], help="3-D: plane-marching (auto) or thread-per-cell")
+    ap.add_argument("--time-step", default="device", choices=["device", "host"],
+                    help="device: dt of step k+1 = cfl_dx / global lambda_max of step k, produced and consumed on the device "
+                         "(exahype_cuda_fv_step_time_loop); host: dt is a host constant and lambda_max is only reduced")
+    ap.add_argument("--cfl-dx", type=float, default=0.4 / 8, help="CFL number x cell size of the device-resident time loop")
+    ap.add_argument("--trace", default="", help="write the exchange's device-side globaltimer stamps of the timed steps to this file (per rank)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--cpu-sample", type=int, default=4096)
@@ -245,7 +250,7 @@ def main():
     import torch
     import torch.distributed as dist
     from exahype_b200 import runtime
-    from exahype_b200.dist import PatchSharding, TimestepReducer
+    from exahype_b200.dist import PatchSharding, TimestepReducer, TimeLoop
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,11 +280,22 @@ def main():
     reducer = TimestepReducer(world, rank, backend=args.reducer) if world > 1 else None
     stream = torch.cuda.current_stream()
 
-    # all-reduce in the patch kernel's own epilogue (peer-memory backend)
-    fused = reducer is not None and reducer.backend == "peer" and not args.no_fused
+    # Device-resident time loop (default): step k+1 runs with dt = cfl_dx / max over ranks of lambda_max(step k); the
+    # exchange is split-phase over NVLink peer memory (published by step k's last warp, consumed by step k+1's warps),
+    # nothing crosses to the host between steps.  It needs the peer-memory reducer at N > 1; with --reducer nccl (or
+    # --time-step host) dt is a host constant and lambda_max is only reduced -- the round-1 loop.
+    peer_ok = reducer is None or reducer.backend == "peer"
+    device_dt = args.time_step == "device" and peer_ok
+    loop = TimeLoop(dtype, reducer, args.cfl_dx, 0.01) if device_dt else None
+    if args.trace and reducer is not None and reducer.backend == "peer":
+        reducer.enable_trace(max(64, 2 * (args.steps + args.warmup) + 16))
+    # host-dt mode: all-reduce in the patch kernel's own epilogue (blocking form, peer-memory backend)
+    fused = (not device_dt) and reducer is not None and reducer.backend == "peer" and not args.no_fused
 
     def step():
-        if fused:
+        if device_dt:
+            upd.step_loop(loop, q_in, q_out, lam_patch)
+        elif fused:
             upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
         else:
             upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
@@ -292,30 +308,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    if reducer is not None:
-        # the collective is exact: the reduced scalar must equal torch.distributed's own MAX over the ranks' local values
-        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
-        local = lam_max.clone()
-        if fused:     # the same step again, reduced by its own epilogue
-            upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
-        else:
-            reducer.allreduce_max(lam_max)
-        dist.all_reduce(local, op=dist.ReduceOp.MAX)
-        torch.cuda.synchronize()
-        if float(local.item()) != float(lam_max.item()) or reducer.timed_out():
-            raise SystemExit(f"rank {rank}: all-reduce(max) mismatch: {float(lam_max.item())} vs {float(local.item())}")
-
+    # The clock sampler starts BEFORE the first warm-up step (nvidia-smi needs a few hundred ms to its first sample), so
+    # that warm-up and timed steps follow each other with nothing but the contract's barrier in between.  This is a
+    # burst measurement like MEASURED_PEAKS.json's copy peak (best of 10): after ~35 ms of back-to-back launches the
+    # board reaches its 1000 W power limit and lowers the SM clock (scripts/clock_trace.py, profiles/); the
+    # `sustained` leg below reports that regime separately.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.5)      # nvidia-smi needs a few hundred ms before its first sample
-    # the sampler's start-up left the device idle for a moment: W more untimed steps right before the timed region.
-    # Kept SHORT on purpose: this is a burst measurement like MEASURED_PEAKS.json's copy peak (best of 10) -- after
-    # ~35 ms of back-to-back launches the board reaches its 1000 W power limit and lowers the SM clock
-    # (scripts/clock_trace.py, profiles/); the `sustained` leg below reports that regime separately.
+        time.sleep(0.5)
+    barrier()
     for _ in range(args.warmup):
         step()
     launches0 = runtime.launch_count()
@@ -326,7 +328,10 @@ def main():
     t_begin.record(stream)
     for i in range(args.steps):
         k_start[i].record(stream)
-        if fused:
+        if device_dt:
+            upd.step_loop(loop, q_in, q_out, lam_patch)
+            k_stop[i].record(stream)
+        elif fused:
             upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
             k_stop[i].record(stream)
         else:
@@ -338,6 +343,29 @@ def main():
     barrier()
     launches = runtime.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if args.trace and reducer is not None and reducer.backend == "peer":
+        first_seq = loop.steps - args.steps + 1 if device_dt else 1
+        np.save(f"{args.trace}.rank{rank}.npy", reducer.read_trace(max(1, first_seq), args.steps))
+
+    # --- correctness of the multi-GPU path, outside the timed region
+    checks = verify_time_loop(torch, dist, upd, reducer, args, q_in, q_out, lam_patch, shard, world, rank) if device_dt else None
+    if loop is not None:
+        loop.flush()
+        torch.cuda.synchronize()
+        hist = loop.history(loop.steps - 1, 2)
+        lam_max.fill_(float(hist[1, 1]))          # the last step's global maximum
+    if reducer is not None and not device_dt:
+        # the collective is exact: the reduced scalar must equal torch.distributed's own MAX over the ranks' local values
+        upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+        local = lam_max.clone()
+        if fused:     # the same step again, reduced by its own epilogue
+            upd.step(q_in, q_out, 0.01, lam_patch, lam_max, reducer=reducer)
+        else:
+            reducer.allreduce_max(lam_max)
+        dist.all_reduce(local, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        if float(local.item()) != float(lam_max.item()) or reducer.timed_out():
+            raise SystemExit(f"rank {rank}: all-reduce(max) mismatch: {float(lam_max.item())} vs {float(local.item())}")
 
     elapsed_ms = t_begin.elapsed_time(t_end)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(k_start, k_stop))
@@ -409,7 +437,7 @@ def main():
                 torch.cuda.synchronize()
                 s2.start()
                 a.record(stream)
-            upd.step(q_in, q_out, 0.01, lam_patch, lam_max)
+            step()
         b.record(stream)
         torch.cuda.synchronize()
         sus_ms = a.elapsed_time(b) / (n_sus - 2 * n_sus // 3)
@@ -430,7 +458,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": desc, "patches_per_gpu": batch, "global_patches": batch * world,
                        "output": args.output, "dissipation": args.dissipation, "layout": "AoS (reference)", "kernel_variant": args.kernel,
-                       "parallelism": f"patch-sharded x{world}" + (f", allreduce-max of lambda per step ({("one-shot NVLink peer-memory exchange in the patch kernel's epilogue" if fused else 'one-shot NVLink peer-memory kernel') if reducer.backend == 'peer' else 'NCCL'})" if world > 1 else ""),
+                       "parallelism": f"patch-sharded x{world}" + (", " + exchange_description(device_dt, fused, reducer) if world > 1 else ""),
+                       "time_step": ("device-derived: dt(k+1) = cfl_dx / global lambda_max(k), produced and consumed on the "
+                                     "device (exahype_cuda_fv_step_time_loop), no host sync between steps") if device_dt
+                                    else "host constant",
+                       "cfl_dx": args.cfl_dx if device_dt else None,
                        "l2": "inputs larger than L2: %.2f GB read + %.2f GB written per step per GPU"
                              % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
                        "kernel": info},
@@ -443,6 +475,8 @@ def main():
             "clocks": clocks,
             "lambda_max": lam_global,
         }
+        if checks is not None:
+            line.update(checks)
         if e2e is not None:
             line["e2e"] = e2e
         if others is not None:
@@ -456,11 +490,77 @@ def main():
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, **cpu_desc}
         print(json.dumps(line), flush=True)
 
+    if loop is not None:
+        loop.close()
     if reducer is not None:
         reducer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def exchange_description(device_dt, fused, reducer):
+    if device_dt:
+        return ("global time step per step: split-phase all-reduce(max) over NVLink peer memory (published by the patch "
+                "kernel's last warp, consumed by the next launch's warps)")
+    if reducer.backend != "peer":
+        return "allreduce-max of lambda per step (NCCL)"
+    return "allreduce-max of lambda per step (" + ("one-shot NVLink peer-memory exchange in the patch kernel's epilogue"
+                                                   if fused else "one-shot NVLink peer-memory kernel") + ")"
+
+
+def verify_time_loop(torch, dist, upd, reducer, args, q_in, q_out, lam_patch, shard, world, rank):
+    """Three steps of a fresh device-resident loop, checked against independent paths (outside the timed region):
+    the global lambda_max the loop consumed == torch.distributed MAX over the ranks' per-patch maxima; the dt it derived ==
+    cfl_dx / that maximum in host arithmetic of the same type; sampled patches of this rank's q_out / lambda_patch ==
+    the CPU oracle run with that dt, bit for bit.  max is exact and every rank divides the same two numbers, so this is
+    the N-GPU == 1-GPU statement of SURVEY.md section 8e on hardware."""
+    import numpy as np
+    import oracle as O        # the checker, never the thing measured
+    from exahype_b200.dist import TimeLoop
+    npdt = np.float64 if upd.dtype == "f64" else np.float32
+    loop = TimeLoop(upd.dtype, reducer, args.cfl_dx, 0.01)
+    for _ in range(3):
+        upd.step_loop(loop, q_in, q_out, lam_patch)
+    loop.flush()
+    torch.cuda.synchronize()
+    hist = loop.history(0, 4)
+    loop.close()
+    lam_ref = lam_patch.max().reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(lam_ref, op=dist.ReduceOp.MAX)            # NCCL: the independent path
+    lam_ref = npdt(lam_ref.item())
+    dt_ref = npdt(args.cfl_dx) / lam_ref
+    ok_lambda = bool(hist[1, 1] == lam_ref and hist[2, 1] == lam_ref and hist[3, 1] == lam_ref and hist[0, 1] == 0)
+    ok_dt = bool(hist[0, 0] == npdt(0.01) and hist[1, 0] == dt_ref and hist[2, 0] == dt_ref and hist[3, 0] == dt_ref)
+    # sampled patches of this shard against the oracle with the dt the device derived
+    n = q_in.shape[0]
+    picks = sorted(set(list(range(min(8, n))) + list(range(n // 2, min(n, n // 2 + 8))) + list(range(max(0, n - 8), n))))
+    cfg = O.OracleConfig(dim=upd.dim, patch_size=upd.patch_size, halo=upd.halo_size, n_real=upd.n_real, n_aux=upd.n_aux,
+                         model=O.MODEL_EULER if upd.model == "euler" else O.MODEL_SWE,
+                         diss=O.DISS_ALL if upd.dissipation == "all" else O.DISS_VAR0)
+    idx = torch.tensor(picks, device=q_in.device)
+    want = q_in[idx].cpu().numpy()
+    # the shard is a slice of ONE global batch: the same bits the oracle generates for those global patch numbers
+    ok_input = all(np.array_equal(want[i], O.fill_synthetic(cfg, 1, first_patch=shard.first + p, dtype=npdt)[0])
+                   for i, p in enumerate(picks[:4]))
+    lam_o, _ = O.step(cfg, want, float(dt_ref), nthreads=2)
+    got = q_out[idx].cpu().numpy()
+    if upd.output == "unhaloed":
+        h = upd.halo_size
+        sl = (slice(None),) + (slice(h, -h),) * upd.dim + (slice(None),)
+        want = want[sl]
+    ok_q = bool(np.array_equal(got, want)) and bool(np.array_equal(lam_patch[idx].cpu().numpy(), lam_o))
+    flags = torch.tensor([ok_lambda, ok_dt, ok_input, ok_q], dtype=torch.int32, device=q_in.device)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ok_lambda, ok_dt, ok_input, ok_q = (bool(x) for x in flags.tolist())
+    timed_out = bool(reducer.timed_out()) if reducer is not None else False
+    return {"multi_gpu_bitwise": bool(ok_lambda and ok_dt and ok_input and ok_q and not timed_out),
+            "time_loop_check": {"global_lambda_equals_nccl_max": ok_lambda, "dt_equals_host_division": ok_dt,
+                                "shard_input_equals_global_batch_slice": ok_input,
+                                "sampled_patches_equal_oracle_bitwise": ok_q, "patches_sampled_per_rank": len(picks),
+                                "dt_device": float(hist[1, 0]), "exchange_timed_out": timed_out}}
 
 
 def synthetic_on_device(torch, upd, first_patch: int, n_patches: int, tdt, device="cuda"):

@@ -27,7 +27,27 @@ cudaError_t peer_reducer_connect(PeerReducer* r, const void* all_handles);
 cudaError_t peer_reducer_allreduce_max(PeerReducer* r, void* value, int dtype, cudaStream_t stream);
 cudaError_t peer_reducer_next_fused(PeerReducer* r, FvPeerFuse* out);
 cudaError_t peer_reducer_error(PeerReducer* r, int* flag);
+cudaError_t peer_reducer_connect_local(PeerReducer* const* all, int world);
+cudaError_t peer_reducer_set_timeout(PeerReducer* r, double seconds);
+cudaError_t peer_reducer_enable_trace(PeerReducer* r, int capacity);
+cudaError_t peer_reducer_read_trace(PeerReducer* r, unsigned long long first_seq, int count, unsigned long long* out);
+int peer_reducer_world(const PeerReducer* r);
+bool peer_reducer_failed(const PeerReducer* r);
+bool peer_reducer_pending(const PeerReducer* r);
 void peer_reducer_destroy(PeerReducer* r);
+struct TimeLoop;      // peer_reduce.cu
+cudaError_t time_loop_create(TimeLoop** out, int dtype, PeerReducer* reducer, double cfl_dx, double dt0, long long history_capacity);
+void time_loop_destroy(TimeLoop* l);
+PeerReducer* time_loop_reducer(TimeLoop* l);
+int time_loop_dtype(const TimeLoop* l);
+long long time_loop_steps(const TimeLoop* l);
+void* time_loop_lambda_acc(TimeLoop* l);
+void* time_loop_dt_device(TimeLoop* l);
+cudaError_t time_loop_next(TimeLoop* l, bool in_kernel_publish, FvPeerFuse* out);
+cudaError_t time_loop_launch_consume(TimeLoop* l, const FvPeerFuse& pf, cudaStream_t stream);
+cudaError_t time_loop_launch_publish(TimeLoop* l, const FvPeerFuse& pf, cudaStream_t stream);
+cudaError_t time_loop_flush(TimeLoop* l, cudaStream_t stream);
+cudaError_t time_loop_history(TimeLoop* l, long long first, long long count, void* out);
 cudaError_t fill_synthetic(const exahype_fv_config* cfg, void* q, long long first_cell, long long n_cells,
                            unsigned long long seed, cudaStream_t stream);   // synthetic.cu
 }
@@ -49,6 +69,14 @@ int fail(int code, const char* fmt, ...) {
 
 int cuda_fail(cudaError_t err, const char* what) {
   return fail(EXAHYPE_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+// a wait of this reducer timed out earlier: everything derived from its exchanges is NaN from then on
+int reducer_failed(const exahype::PeerReducer* r) {
+  if (r && exahype::peer_reducer_failed(r))
+    return fail(EXAHYPE_ERR_TIMEOUT, "a peer never arrived at an all-reduce(max) exchange (wait timed out): the reduced "
+                                     "scalar and every time step derived from it are NaN; destroy the reducer");
+  return EXAHYPE_OK;
 }
 
 const std::vector<exahype::FvEntry>& registry() {
@@ -209,8 +237,10 @@ int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, 
   cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches > 0 ? n_patches : 1);
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_allreduce (launch info)");
   exahype::PeerReducer* r = static_cast<exahype::PeerReducer*>(reducer);
-  if (!info.fused_allreduce || n_patches <= 0) {
-    // kernels without the fused epilogue (and empty shards): the step, then the stand-alone one-shot kernel
+  if ((rc = reducer_failed(r))) return rc;
+  if (!info.fused_allreduce || n_patches <= 0 || exahype::peer_reducer_world(r) > 32) {
+    // kernels without the fused epilogue, empty shards, more than 32 ranks (the epilogue has one lane per peer): the
+    // step, then the stand-alone one-shot kernel
     rc = exahype_cuda_fv_step(cfg, q_in, q_out, n_patches, dt, lambda_patch, lambda_max, stream);
     if (rc) return rc;
     return exahype_cuda_peer_reducer_allreduce_max(reducer, lambda_max, cfg->dtype, stream);
@@ -227,7 +257,7 @@ int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, 
   }
   exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}};
   err = exahype::peer_reducer_next_fused(r, &g.peer);
-  if (err != cudaSuccess) return cuda_fail(err, "peer reducer not connected (or more than 32 ranks)");
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer not connected, or a time loop's exchange is still pending (flush it)");
   err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, &g);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (fused all-reduce)");
   g_launches.fetch_add(1);
@@ -289,24 +319,32 @@ struct HostPipeline {
   }
 };
 
-std::mutex g_pipe_mutex;
-HostPipeline g_pipe;
-long long g_chunk_patches = 0;   // 0: derive from a ~32 MiB input chunk
-int g_depth = 3;
+// One pipeline per device, each behind its own mutex: host threads driving different GPUs neither serialise nor evict
+// each other's staging buffers (two calls for the SAME device do serialise: they share its staging ring).
+struct DevicePipeline {
+  std::mutex mutex;
+  HostPipeline pipe;
+};
+constexpr int kMaxDevices = 64;
+DevicePipeline g_pipes[kMaxDevices];
+std::atomic<long long> g_chunk_patches{0};   // 0: derive from a ~32 MiB input chunk
+std::atomic<int> g_depth{3};
 
 }  // namespace
 
 int exahype_cuda_host_pipeline_configure(int64_t chunk_patches, int depth) {
-  std::lock_guard<std::mutex> lock(g_pipe_mutex);
   if (chunk_patches < 0 || depth < 0 || depth > 8) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "bad pipeline configuration");
   g_chunk_patches = chunk_patches;
-  if (depth > 0) g_depth = depth;
+  g_depth = depth > 0 ? depth : 3;
   return EXAHYPE_OK;
 }
 
 int exahype_cuda_host_pipeline_release(void) {
-  std::lock_guard<std::mutex> lock(g_pipe_mutex);
-  g_pipe.release();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return EXAHYPE_OK; }   // no device: nothing was cached
+  if (dev < 0 || dev >= kMaxDevices) return EXAHYPE_OK;
+  std::lock_guard<std::mutex> lock(g_pipes[dev].mutex);
+  g_pipes[dev].pipe.release();
   return EXAHYPE_OK;
 }
 
@@ -325,14 +363,16 @@ int exahype_cuda_time_step_host(const exahype_fv_config* cfg, const void* q_host
   const size_t in_patch = (size_t)ipow_ll(cfg->patch_size + 2 * cfg->halo, cfg->dim) * nv * es;
   const size_t out_patch = unhaloed ? (size_t)ipow_ll(cfg->patch_size, cfg->dim) * nv * es : in_patch;
 
-  std::lock_guard<std::mutex> lock(g_pipe_mutex);
   int dev = 0;
   cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
-  long long chunk = g_chunk_patches > 0 ? g_chunk_patches : std::max<long long>(1, (long long)((32u << 20) / in_patch));
+  if (dev < 0 || dev >= kMaxDevices) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_pipes[dev].mutex);
+  const long long configured = g_chunk_patches.load();
+  long long chunk = configured > 0 ? configured : std::max<long long>(1, (long long)((32u << 20) / in_patch));
   chunk = std::min<long long>(chunk, std::max<long long>(n_patches, 1));
-  const int depth = g_depth;
-  HostPipeline& p = g_pipe;
+  const int depth = g_depth.load();
+  HostPipeline& p = g_pipes[dev].pipe;
   if (p.device != dev || p.depth != depth || p.in_capacity < (size_t)chunk * in_patch ||
       p.out_capacity < (size_t)chunk * out_patch || p.lam_capacity < (size_t)chunk * es) {
     p.release();
@@ -512,8 +552,11 @@ int exahype_cuda_peer_reducer_connect(void* reducer, const void* all_handles) {
 int exahype_cuda_peer_reducer_allreduce_max(void* reducer, void* value, int dtype, void* stream) {
   if (!reducer || !value) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / value");
   if (dtype != EXAHYPE_DTYPE_F64 && dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  if (int rc = reducer_failed(static_cast<exahype::PeerReducer*>(reducer))) return rc;
   cudaError_t err = exahype::peer_reducer_allreduce_max(static_cast<exahype::PeerReducer*>(reducer), value, dtype,
                                                         static_cast<cudaStream_t>(stream));
+  if (err == cudaErrorNotReady)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "peer reducer not connected, or a time loop's exchange is still pending (flush it)");
   if (err != cudaSuccess) return cuda_fail(err, "peer_allreduce_max_kernel launch");
   g_launches.fetch_add(1);
   return EXAHYPE_OK;
@@ -526,8 +569,138 @@ int exahype_cuda_peer_reducer_status(void* reducer, int* flag) {
   return EXAHYPE_OK;
 }
 
+int exahype_cuda_peer_reducer_set_timeout(void* reducer, double seconds) {
+  if (!reducer || !(seconds > 0.0)) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / non-positive timeout");
+  cudaError_t err = exahype::peer_reducer_set_timeout(static_cast<exahype::PeerReducer*>(reducer), seconds);
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer timeout");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_connect_local(void* const* reducers, int world_size) {
+  if (!reducers || world_size < 1) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducers / bad world size");
+  cudaError_t err = exahype::peer_reducer_connect_local(reinterpret_cast<exahype::PeerReducer* const*>(reducers), world_size);
+  if (err != cudaSuccess) return cuda_fail(err, "peer_reducer_connect_local (reducers must be ranks 0..world-1 of one world)");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_enable_trace(void* reducer, int capacity) {
+  if (!reducer || capacity < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / negative capacity");
+  cudaError_t err = exahype::peer_reducer_enable_trace(static_cast<exahype::PeerReducer*>(reducer), capacity);
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer trace buffer");
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_peer_reducer_read_trace(void* reducer, uint64_t first_seq, int count, uint64_t* out) {
+  if (!reducer || !out || count < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null reducer / out");
+  static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "uint64_t");
+  cudaError_t err = exahype::peer_reducer_read_trace(static_cast<exahype::PeerReducer*>(reducer), first_seq, count,
+                                                     reinterpret_cast<unsigned long long*>(out));
+  if (err != cudaSuccess) return cuda_fail(err, "peer reducer trace (enabled? count <= capacity?)");
+  return EXAHYPE_OK;
+}
+
 int exahype_cuda_peer_reducer_destroy(void* reducer) {
   exahype::peer_reducer_destroy(static_cast<exahype::PeerReducer*>(reducer));
+  return EXAHYPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident time loop (peer_reduce.cu, peer_mail.cuh)
+int exahype_cuda_time_loop_create(void** loop, int dtype, void* reducer, double cfl_dx, double dt0,
+                                  int64_t history_capacity) {
+  if (!loop) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "loop is null");
+  if (dtype != EXAHYPE_DTYPE_F64 && dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  if (!(cfl_dx > 0.0) || history_capacity < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cfl_dx must be > 0 and history_capacity >= 0");
+  if (int rc = reducer_failed(static_cast<exahype::PeerReducer*>(reducer))) return rc;
+  exahype::TimeLoop* l = nullptr;
+  cudaError_t err = exahype::time_loop_create(&l, dtype, static_cast<exahype::PeerReducer*>(reducer), cfl_dx, dt0, history_capacity);
+  if (err != cudaSuccess) return cuda_fail(err, "time_loop_create");
+  *loop = l;
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_fv_step_time_loop(const exahype_fv_config* cfg, void* loop, const void* q_in, void* q_out,
+                                   int64_t n_patches, void* lambda_patch, void* stream) {
+  const exahype::FvEntry* e = nullptr;
+  int rc = lookup(cfg, &e);
+  if (rc) return rc;
+  if (!loop) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "loop is null");
+  exahype::TimeLoop* l = static_cast<exahype::TimeLoop*>(loop);
+  exahype::PeerReducer* r = exahype::time_loop_reducer(l);
+  if ((rc = reducer_failed(r))) return rc;
+  if (cfg->dtype != exahype::time_loop_dtype(l)) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "the loop's dtype differs from cfg->dtype");
+  if (cfg->flags & EXAHYPE_FLAG_LAMBDA_ACCUMULATE) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "the loop owns lambda_max: no LAMBDA_ACCUMULATE");
+  if (n_patches < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_patches must be >= 0 (got %lld)", (long long)n_patches);
+  if (n_patches > 0) {
+    if (!q_in || !q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must not be null");
+    if ((reinterpret_cast<uintptr_t>(q_in) & 15) || (reinterpret_cast<uintptr_t>(q_out) & 15))
+      return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must be 16-byte aligned (TMA bulk copies)");
+    if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
+      return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
+  }
+  const int var = variant_of(cfg->flags);
+  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  exahype::FvLaunchInfo info;
+  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches > 0 ? n_patches : 1);
+  if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_time_loop (launch info)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool in_kernel = info.fused_allreduce && n_patches > 0 && exahype::peer_reducer_world(r) <= 32;
+  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}};
+  err = exahype::time_loop_next(l, in_kernel, &g.peer);
+  if (err != cudaSuccess) return cuda_fail(err, "time loop: reducer not connected");
+  if (n_patches > 0) {
+    // dt by value is unused (the kernel reads / derives it on the device); lambda_max is the loop's accumulator
+    err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, 0.0, lambda_patch,
+                                                     exahype::time_loop_lambda_acc(l), s, &g);
+    if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (time loop)");
+    g_launches.fetch_add(1);
+  } else {
+    err = exahype::time_loop_launch_consume(l, g.peer, s);       // an empty shard still takes part in the exchange
+    if (err != cudaSuccess) return cuda_fail(err, "loop_consume_kernel launch");
+    g_launches.fetch_add(1);
+  }
+  if (!in_kernel) {
+    err = exahype::time_loop_launch_publish(l, g.peer, s);
+    if (err != cudaSuccess) return cuda_fail(err, "loop_publish_kernel launch");
+    g_launches.fetch_add(1);
+  }
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_time_loop_flush(void* loop, void* stream) {
+  if (!loop) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "loop is null");
+  exahype::TimeLoop* l = static_cast<exahype::TimeLoop*>(loop);
+  if (int rc = reducer_failed(exahype::time_loop_reducer(l))) return rc;
+  const bool pending = exahype::peer_reducer_pending(exahype::time_loop_reducer(l));
+  cudaError_t err = exahype::time_loop_flush(l, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "loop_consume_kernel launch (flush)");
+  if (pending) g_launches.fetch_add(1);
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_time_loop_history(void* loop, int64_t first_step, int64_t count, void* out) {
+  if (!loop || !out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null loop / out");
+  exahype::TimeLoop* l = static_cast<exahype::TimeLoop*>(loop);
+  cudaError_t err = exahype::time_loop_history(l, first_step, count, out);
+  if (err == cudaErrorInvalidValue)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "history range [%lld, %lld) outside the recorded steps / capacity",
+                (long long)first_step, (long long)(first_step + count));
+  if (err != cudaSuccess) return cuda_fail(err, "time loop history");
+  return reducer_failed(exahype::time_loop_reducer(l));
+}
+
+int64_t exahype_cuda_time_loop_steps(void* loop) {
+  return loop ? exahype::time_loop_steps(static_cast<exahype::TimeLoop*>(loop)) : 0;
+}
+
+int exahype_cuda_time_loop_dt_device(void* loop, void** dt_device) {
+  if (!loop || !dt_device) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "null loop / dt_device");
+  *dt_device = exahype::time_loop_dt_device(static_cast<exahype::TimeLoop*>(loop));
+  return EXAHYPE_OK;
+}
+
+int exahype_cuda_time_loop_destroy(void* loop) {
+  exahype::time_loop_destroy(static_cast<exahype::TimeLoop*>(loop));
   return EXAHYPE_OK;
 }
 

@@ -272,6 +272,8 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   const long long unit = (long long)blockIdx.x * C::WPC + warp;     // one unit = PPW consecutive patches
   const long long first_patch = unit * PPW;
   if (first_patch >= n_patches) return;                             // whole warp leaves together
+  // device-resident time step (peer_mail.cuh): every warp derives the same dt from this device's mailbox
+  dt = peer_loop_dt<T>(gather.peer, lane, dt, unit == 0);
 
   RowMarch<C> m;
   m.X = reinterpret_cast<T*>(smem + warp * C::WARP_BYTES);

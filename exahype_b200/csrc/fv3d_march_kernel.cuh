@@ -381,6 +381,8 @@ fv3d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   using Bits = typename FloatBits<T>::type;
   constexpr int P = C::P, H = C::H, S = C::S, NV = C::NV, NR = C::NR, R = C::R, NPL = C::NPL;
 
+  // device-resident time step (peer_mail.cuh): every warp derives the same dt from this device's mailbox
+  dt = peer_loop_dt<T>(gather.peer, (int)(threadIdx.x & 31), dt, blockIdx.x == 0 && threadIdx.x < 32);
   extern __shared__ __align__(128) unsigned char smem[];
   const int group = threadIdx.x / C::GROUP_THREADS;
   const int gt = threadIdx.x - group * C::GROUP_THREADS;      // thread within the group

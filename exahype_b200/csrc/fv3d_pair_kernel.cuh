@@ -506,6 +506,12 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
     }
   T lam_local = T(0), warp_lam = T(0);
 
+  const bool first_warp = (w_index == 0);
+  if (first_warp && lane == 0 && gather.peer.mode == FV_PEER_LOOP) peer_trace(gather.peer, gather.peer.seq, FV_TRACE_KERNEL_BEGIN);
+  // Device-resident time step (peer_mail.cuh): the ring is requested, the lane geometry is set up; a wait for the
+  // slowest peer's maximum of the previous step overlaps this launch's start-up and the first planes' flight from HBM
+  // instead of having extended the previous launch.
+  if (ps.n_my_patches > 0) ps.dt = peer_loop_dt<T>(gather.peer, lane, ps.dt, first_warp);
   for (; ps.pi < ps.n_my_patches; ++ps.pi) {
     ps.begin_patch(gather, ps.pi == 0);
     pair_pre_step<C, 0>(ps, gather, ln, w);
@@ -527,7 +533,9 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   }
   // multi-GPU: the global admissible-time-step scalar in the same launch -- the last warp of the grid to get here
   // exchanges this device's maximum with every peer over NVLink (peer_mail.cuh) and leaves the result in *lambda_max
-  if (gather.peer.world > 1) fused_allreduce_max<T, Bits>(gather.peer, lambda_max, lane, gridDim.x * (unsigned)C::NW);
+  // (blocking), or only publishes it for the next launch's warps to consume (time loop)
+  if (gather.peer.mode == FV_PEER_BLOCKING || gather.peer.mode == FV_PEER_LOOP)
+    fused_allreduce_max<T, Bits>(gather.peer, lambda_max, lane, gridDim.x * (unsigned)C::NW);
 }
 
 template <class C>

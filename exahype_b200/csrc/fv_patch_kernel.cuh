@@ -56,8 +56,9 @@ struct FvGather {
   const T* const* q_in = nullptr;
   T* const* q_out = nullptr;
   const T* dt = nullptr;
-  // multi-GPU: the all-reduce(max) of lambda_max run by the kernel's own epilogue (kernels whose launch info says
-  // fused_allreduce; world <= 1: none).  Rides along here because this struct already reaches every kernel.
+  // the step's time-step source and the all-reduce(max) of lambda_max (peer_mail.cuh): every kernel honours
+  // peer.dt_in (device-resident dt); kernels whose launch info says fused_allreduce also run the exchange themselves
+  // (peer.mode).  Rides along here because this struct already reaches every kernel.
   FvPeerFuse peer;
   template <bool GATHER>
   __device__ __forceinline__ const T* in(const T* base, long long patch, int patch_elems) const {
@@ -276,6 +277,8 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
   constexpr int DIM = C::DIM, NV = C::NV, NR = C::NR, G = C::G, NT = C::NT, CPT = C::CPT;
   constexpr int FSTRIDE = G * C::SLOTS;   // elements per (axis, variable) plane of the flux scratch
 
+  // device-resident time step (peer_mail.cuh): every warp derives the same dt from this device's mailbox
+  dt = peer_loop_dt<T>(gather.peer, (int)(threadIdx.x & 31), dt, blockIdx.x == 0 && threadIdx.x < 32);
   extern __shared__ __align__(128) unsigned char smem[];
   T* const qbuf = reinterpret_cast<T*>(smem + C::OFF_Q);
   T* const Fs = reinterpret_cast<T*>(smem + C::OFF_F);

@@ -156,12 +156,33 @@ class TimestepReducer:
         return self._peer if self._peer else None
 
     def timed_out(self) -> bool:
-        """True if a peer-memory wait gave up (a rank never arrived).  Synchronises the device."""
+        """True if a peer-memory wait gave up (a rank never arrived): the waiting side's result is NaN and every later
+        call on this reducer raises ``TIMEOUT``.  The flag lives in host-mapped memory -- nothing is synchronised."""
         if not self._peer:
             return False
         flag = ctypes.c_int(0)
         self._lib.exahype_cuda_peer_reducer_status(self._peer, ctypes.byref(flag))
         return bool(flag.value)
+
+    def set_timeout(self, seconds: float):
+        """How long a peer-memory wait spins before it gives up (default 10 s)."""
+        if self._peer:
+            from . import runtime
+            runtime.check(self._lib.exahype_cuda_peer_reducer_set_timeout(self._peer, float(seconds)), self._lib)
+
+    def enable_trace(self, capacity: int = 1024):
+        """Keep device-side ``globaltimer`` stamps of the last ``capacity`` exchanges (csrc/peer_mail.cuh FV_TRACE_*)."""
+        if self._peer:
+            from . import runtime
+            runtime.check(self._lib.exahype_cuda_peer_reducer_enable_trace(self._peer, int(capacity)), self._lib)
+
+    def read_trace(self, first_seq: int, count: int):
+        """``[count, 8]`` uint64 array of the stamps of exchanges ``first_seq ..`` (synchronises the device)."""
+        import numpy as np
+        from . import runtime
+        out = np.zeros((count, 8), dtype=np.uint64)
+        runtime.check(self._lib.exahype_cuda_peer_reducer_read_trace(self._peer, first_seq, count, out.ctypes.data), self._lib)
+        return out
 
     def close(self):
         if self._lib is None:
@@ -172,3 +193,122 @@ class TimestepReducer:
         if self._comm:
             self._lib.exahype_cuda_comm_destroy(self._comm)
             self._comm = ctypes.c_void_p()
+
+
+class TimeLoop:
+    """Device-resident time loop (``exahype_cuda_time_loop_*``): step ``k+1`` advances with
+    ``dt = cfl_dx / max over all ranks of lambda_max(step k)``, produced and consumed on the device -- no host round
+    trip, no memset and (for the warp-per-patch kernel) no second kernel between two steps.  The exchange is
+    split-phase: step ``k``'s last warp publishes into every peer's mailbox, step ``k+1``'s warps consume.
+
+    ``reducer``: a :class:`TimestepReducer` with the peer-memory backend (all its ranks step in lockstep) or ``None``
+    for one GPU.  Drive it with :meth:`exahype_b200.runtime.PatchUpdate.step_loop`.
+    """
+
+    def __init__(self, dtype: str = "f64", reducer: "TimestepReducer | None" = None, cfl_dx: float = 1.0,
+                 dt0: float = 0.0, history_capacity: int = 0, peer_handle=None):
+        from . import runtime
+        self._lib = runtime.load()
+        self.dtype = dtype
+        self.cfl_dx, self.dt0 = float(cfl_dx), float(dt0)
+        self.handle = ctypes.c_void_p()
+        if reducer is not None and peer_handle is None:
+            peer_handle = reducer.peer_handle
+            if peer_handle is None and reducer.world_size > 1:
+                raise RuntimeError("the device-resident time loop needs the peer-memory reducer (backend='peer')")
+        self._reducer = reducer
+        runtime.check(self._lib.exahype_cuda_time_loop_create(ctypes.byref(self.handle), runtime.DTYPE[dtype], peer_handle,
+                                                              self.cfl_dx, self.dt0, int(history_capacity)), self._lib)
+
+    @property
+    def steps(self) -> int:
+        return int(self._lib.exahype_cuda_time_loop_steps(self.handle))
+
+    def flush(self, stream=None):
+        """Consume the exchange still in flight: afterwards :meth:`dt_device` holds the NEXT step's dt."""
+        import torch
+        from . import runtime
+        if stream is None:
+            stream = torch.cuda.current_stream().cuda_stream
+        runtime.check(self._lib.exahype_cuda_time_loop_flush(self.handle, stream), self._lib)
+
+    def history(self, first: int = 0, count: "int | None" = None):
+        """``[count, 4]`` array: per step ``{dt used, global lambda_max it was derived from (0: dt0), this device's
+        lambda_max of the step, 0}``; entry ``steps`` (after :meth:`flush`) is ``{next dt, last global lambda_max}``.
+        Synchronises the device."""
+        import numpy as np
+        from . import runtime
+        if count is None:
+            count = self.steps - first
+        out = np.zeros((count, 4), dtype=np.float64 if self.dtype == "f64" else np.float32)
+        runtime.check(self._lib.exahype_cuda_time_loop_history(self.handle, first, count, out.ctypes.data), self._lib)
+        return out
+
+    def dt_device(self) -> int:
+        """Device address of the scalar holding the most recently established time step."""
+        from . import runtime
+        p = ctypes.c_void_p()
+        runtime.check(self._lib.exahype_cuda_time_loop_dt_device(self.handle, ctypes.byref(p)), self._lib)
+        return p.value
+
+    def close(self):
+        if self.handle:
+            self._lib.exahype_cuda_time_loop_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+class LocalPeerGroup:
+    """``world_size`` peer-memory reducers living in THIS process on the current device, connected to each other
+    through plain device pointers (``exahype_cuda_peer_reducer_connect_local``).  The same mailbox protocol and the
+    same kernels as one process per GPU, minus NVLink: what the 1-GPU tests drive (each "rank" on its own stream), and
+    the way to run several ranks per GPU.  ``group[r]`` quacks like a :class:`TimestepReducer` with the peer backend."""
+
+    class Rank:
+        backend = "peer"
+
+        def __init__(self, group, rank, handle):
+            self._group, self.rank, self.world_size, self._peer, self._lib = group, rank, group.world_size, handle, group._lib
+
+        @property
+        def peer_handle(self):
+            return self._peer
+
+        def allreduce_max(self, value, stream=None):
+            import torch
+            from . import runtime
+            if stream is None:
+                stream = torch.cuda.current_stream(value.device).cuda_stream
+            dtype = {torch.float64: 0, torch.float32: 1}[value.dtype]
+            runtime.check(self._lib.exahype_cuda_peer_reducer_allreduce_max(self._peer, value.data_ptr(), dtype, stream),
+                          self._lib)
+            return value
+
+        timed_out = TimestepReducer.timed_out
+        set_timeout = TimestepReducer.set_timeout
+        enable_trace = TimestepReducer.enable_trace
+        read_trace = TimestepReducer.read_trace
+
+    def __init__(self, world_size: int):
+        from . import runtime
+        self._lib = runtime.load()
+        self.world_size = world_size
+        handles = (ctypes.c_void_p * world_size)()
+        self.ranks = []
+        for r in range(world_size):
+            h = ctypes.c_void_p()
+            runtime.check(self._lib.exahype_cuda_peer_reducer_create(ctypes.byref(h), world_size, r), self._lib)
+            handles[r] = h.value
+            self.ranks.append(LocalPeerGroup.Rank(self, r, h))
+        runtime.check(self._lib.exahype_cuda_peer_reducer_connect_local(handles, world_size), self._lib)
+
+    def __getitem__(self, r):
+        return self.ranks[r]
+
+    def __len__(self):
+        return self.world_size
+
+    def close(self):
+        for rk in self.ranks:
+            if rk._peer:
+                self._lib.exahype_cuda_peer_reducer_destroy(rk._peer)
+                rk._peer = ctypes.c_void_p()

@@ -28,7 +28,7 @@ FLAG_OUTPUT_UNHALOED = 1 << 1
 FLAG_LAMBDA_ACCUMULATE = 1 << 2
 FLAG_KERNEL_CELL = 1 << 3
 
-ERR_NAMES = {-1: "INVALID_ARGUMENT", -2: "NO_INSTANTIATION", -3: "CUDA", -4: "NCCL", -5: "UNAVAILABLE"}
+ERR_NAMES = {-1: "INVALID_ARGUMENT", -2: "NO_INSTANTIATION", -3: "CUDA", -4: "NCCL", -5: "UNAVAILABLE", -6: "TIMEOUT"}
 
 
 class ExaHyPECudaError(RuntimeError):
@@ -89,6 +89,18 @@ def load(path: Optional[str] = None) -> ctypes.CDLL:
     lib.exahype_cuda_peer_reducer_allreduce_max.argtypes = [vp, vp, i32, vp]
     lib.exahype_cuda_peer_reducer_status.argtypes = [vp, ip]
     lib.exahype_cuda_peer_reducer_destroy.argtypes = [vp]
+    lib.exahype_cuda_peer_reducer_set_timeout.argtypes = [vp, dbl]
+    lib.exahype_cuda_peer_reducer_connect_local.argtypes = [ctypes.POINTER(vp), i32]
+    lib.exahype_cuda_peer_reducer_enable_trace.argtypes = [vp, i32]
+    lib.exahype_cuda_peer_reducer_read_trace.argtypes = [vp, ctypes.c_uint64, i32, vp]
+    lib.exahype_cuda_time_loop_create.argtypes = [ctypes.POINTER(vp), i32, vp, dbl, dbl, i64]
+    lib.exahype_cuda_fv_step_time_loop.argtypes = [c_cfg, vp, vp, vp, i64, vp, vp]
+    lib.exahype_cuda_time_loop_flush.argtypes = [vp, vp]
+    lib.exahype_cuda_time_loop_history.argtypes = [vp, i64, i64, vp]
+    lib.exahype_cuda_time_loop_steps.argtypes = [vp]
+    lib.exahype_cuda_time_loop_steps.restype = i64
+    lib.exahype_cuda_time_loop_dt_device.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.exahype_cuda_time_loop_destroy.argtypes = [vp]
     for t, ct in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
         for name in (f"exahype_cuda_fv_step_euler_2d_{t}", f"exahype_cuda_fv_step_euler_3d_{t}",
                      f"exahype_cuda_fv_step_swe_2d_{t}"):
@@ -268,6 +280,36 @@ class PatchUpdate:
                     lambda_max.data_ptr() if lambda_max is not None else None, stream), self._lib)
         if reducer is not None and not fused:
             reducer.allreduce_max(lambda_max, stream=stream)
+        return q_out
+
+    def step_loop(self, loop, q_in, q_out, lambda_patch=None, stream=None):
+        """One step of a device-resident time loop (:class:`exahype_b200.dist.TimeLoop`,
+        ``exahype_cuda_fv_step_time_loop``): like :meth:`step`, but dt is the loop's -- ``cfl_dx / lambda_max`` of the
+        previous step over all ranks, derived on the device -- and this step's ``lambda_max`` goes into the loop's
+        exchange.  Collective across the loop's ranks.  ``q_in`` may be an empty shard."""
+        import torch
+        tdt = torch.float64 if self.dtype == "f64" else torch.float32
+        if loop.dtype != self.dtype:
+            raise ValueError(f"the loop runs in {loop.dtype}, this update in {self.dtype}")
+        for name, t in (("q_in", q_in), ("q_out", q_out), ("lambda_patch", lambda_patch)):
+            if t is None:
+                continue
+            if t.dtype != tdt or not t.is_contiguous() or not t.is_cuda or t.device != q_in.device:
+                raise ValueError(f"{name} must be a contiguous {tdt} CUDA tensor on {q_in.device}")
+        n = self._n_patches(q_in.numel())
+        if q_out is not q_in and q_out.numel() != int(np.prod(self.out_shape(n))):
+            raise ValueError(f"q_out must hold {self.out_shape(n)}")
+        if q_out is q_in and self.output != "haloed":
+            raise ValueError("un-haloed output needs its own q_out")
+        if lambda_patch is not None and lambda_patch.numel() < n:
+            raise ValueError("lambda_patch must hold one value per patch")
+        if stream is None:
+            stream = torch.cuda.current_stream(q_in.device).cuda_stream
+        c = self.config()
+        with torch.cuda.device(q_in.device):
+            check(self._lib.exahype_cuda_fv_step_time_loop(
+                ctypes.byref(c), loop.handle, q_in.data_ptr() if n else None, q_out.data_ptr() if n else None, n,
+                lambda_patch.data_ptr() if lambda_patch is not None else None, stream), self._lib)
         return q_out
 
     def step_cell_data(self, q_in_ptrs, q_out_ptrs, dt=0.0, dt_patch=None, max_eigenvalue=None, lambda_max=None,

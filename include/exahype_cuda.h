@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EXAHYPE_CUDA_ABI_VERSION 1
+#define EXAHYPE_CUDA_ABI_VERSION 2
 
 enum {
   EXAHYPE_OK = 0,
@@ -36,7 +36,8 @@ enum {
   EXAHYPE_ERR_NO_INSTANTIATION = -2, /* no committed kernel for this (model, dim, patch, halo, vars, dtype): generate one with CUDAPrinter */
   EXAHYPE_ERR_CUDA = -3,             /* CUDA runtime error (message carries cudaGetErrorString) */
   EXAHYPE_ERR_NCCL = -4,
-  EXAHYPE_ERR_UNAVAILABLE = -5       /* optional component missing (e.g. libnccl not loadable) */
+  EXAHYPE_ERR_UNAVAILABLE = -5,      /* optional component missing (e.g. libnccl not loadable) */
+  EXAHYPE_ERR_TIMEOUT = -6           /* a peer never arrived at an exchange: results derived from it are NaN (sticky) */
 };
 
 /* physics families with committed hand-written functors (csrc/physics.cuh) */
@@ -134,6 +135,8 @@ int exahype_cuda_fv_step_swe_2d_f32(const float* q_in, float* q_out, int64_t n_p
  * overlapped on internal streams.  q_host is updated in place (haloed) or q_out_host receives the result
  * (layout per flags; may equal q_host when haloed).  lambda_max_host (nullable) receives the batch maximum.
  * Pinned host memory gives full PCIe bandwidth; pageable memory works.  Synchronous: returns when done.
+ * Thread-safe: the staging ring is per device (the caller's current device); host threads driving different GPUs run
+ * concurrently, two calls for the same device serialise.
  */
 int exahype_cuda_time_step_host(const exahype_fv_config* cfg, const void* q_host, void* q_out_host,
                                 int64_t n_patches, double dt, void* lambda_patch_host, void* lambda_max_host);
@@ -178,13 +181,23 @@ int exahype_cuda_allreduce_max(void* comm, void* values, int64_t count, int dtyp
  *   local_handle  writes the 64-byte cudaIpcMemHandle_t of the mailbox (the host plumbing all-gathers them)
  *   connect       maps the world_size * 64 bytes of gathered handles (own entry ignored)
  *   allreduce_max in place on the device scalar `value` of dtype, asynchronous on stream
- *   status        *flag = 1 if a wait timed out (a peer never arrived); synchronises the device
+ *   status        *flag = 1 if a wait timed out (a peer never arrived).  The flag lives in host-mapped memory: reading it
+ *                 synchronises nothing, and every later call on the reducer (or a time loop built on it) fails with
+ *                 EXAHYPE_ERR_TIMEOUT.  The waiting side's result is NaN, never a silently rank-local value.
+ *   set_timeout   how long a wait spins before it gives up (default 10 s)
+ *   connect_local test / several-ranks-per-GPU form of connect: all `world_size` reducers live in this process on one device
+ *   enable_trace  keep globaltimer stamps of the last `capacity` exchanges (see csrc/peer_mail.cuh FV_TRACE_*);
+ *   read_trace    host copy of count rows of 8 uint64 starting at exchange first_seq (synchronises the device)
  */
 int exahype_cuda_peer_reducer_create(void** reducer, int world_size, int rank);
 int exahype_cuda_peer_reducer_local_handle(void* reducer, void* handle64);
 int exahype_cuda_peer_reducer_connect(void* reducer, const void* all_handles);
 int exahype_cuda_peer_reducer_allreduce_max(void* reducer, void* value, int dtype, void* stream);
 int exahype_cuda_peer_reducer_status(void* reducer, int* flag);
+int exahype_cuda_peer_reducer_set_timeout(void* reducer, double seconds);
+int exahype_cuda_peer_reducer_connect_local(void* const* reducers, int world_size);
+int exahype_cuda_peer_reducer_enable_trace(void* reducer, int capacity);
+int exahype_cuda_peer_reducer_read_trace(void* reducer, uint64_t first_seq, int count, uint64_t* out);
 /*
  * exahype_cuda_fv_step followed by exahype_cuda_peer_reducer_allreduce_max(lambda_max), as ONE launch where the shape's
  * kernel supports it (the warp-per-patch kernel of 8x8x8 patches): the last warp of the grid to finish exchanges the
@@ -196,6 +209,38 @@ int exahype_cuda_peer_reducer_status(void* reducer, int* flag);
 int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, const void* q_in, void* q_out,
                                    int64_t n_patches, double dt, void* lambda_patch, void* lambda_max, void* stream);
 int exahype_cuda_peer_reducer_destroy(void* reducer);
+
+/*
+ * Device-resident time loop: the global admissible time step of SURVEY.md section 8e, produced AND consumed on the
+ * device.  Step k+1 advances with dt = cfl_dx / max over all ranks of lambda_max(step k), where lambda_max(step k) is the
+ * largest eigenvalue of step k's input state (a8).  Nothing crosses to the host between steps, there is no memset and
+ * no second kernel between two steps of the warp-per-patch kernel, and the exchange is split-phase: the last warp of
+ * step k's grid stores this device's maximum into every peer's mailbox (NVLink peer memory, csrc/peer_mail.cuh) and
+ * the launch ends; the warps of step k+1 read the mailbox right before their first use of dt, so waiting for the
+ * slowest rank overlaps step k+1's start-up.  max is exact and all ranks divide the same two numbers: an N-GPU run
+ * takes bit for bit the time steps of the 1-GPU run.  The reference has no counterpart: its `time_step(Q, dt)` takes
+ * dt by value ("Unit test/test.h":3) and Peano derives the next dt on the host.
+ *   create    dtype EXAHYPE_DTYPE_*; reducer: a connected peer reducer (all ranks step in lockstep), or NULL for this
+ *             device alone; cfl_dx = CFL number x cell size; dt0 = time step of the first step;
+ *             history_capacity = steps remembered (0: 4096)
+ *   step      as exahype_cuda_fv_step, with dt and lambda_max owned by the loop.  Shapes whose kernel has no exchange
+ *             epilogue (and empty shards) run the same protocol with a one-warp kernel behind the patch kernel.
+ *             Collective across the reducer's ranks: every rank calls it once per step.
+ *   flush     consumes the exchange still in flight (a one-warp kernel): afterwards dt_device holds the NEXT step's dt
+ *   history   host copy of entries [first_step, first_step + count), 4 values of dtype each: {dt used by the step, the
+ *             global maximum it was derived from (0: none, dt0 was used), this device's lambda_max of the step, 0}.
+ *             Entry `steps` (after flush) holds {next dt, last global maximum}.  Synchronises the device.
+ *   steps     steps launched so far;  dt_device: device scalar with the most recently established dt
+ */
+int exahype_cuda_time_loop_create(void** loop, int dtype, void* reducer, double cfl_dx, double dt0,
+                                  int64_t history_capacity);
+int exahype_cuda_fv_step_time_loop(const exahype_fv_config* cfg, void* loop, const void* q_in, void* q_out,
+                                   int64_t n_patches, void* lambda_patch, void* stream);
+int exahype_cuda_time_loop_flush(void* loop, void* stream);
+int exahype_cuda_time_loop_history(void* loop, int64_t first_step, int64_t count, void* out);
+int64_t exahype_cuda_time_loop_steps(void* loop);
+int exahype_cuda_time_loop_dt_device(void* loop, void** dt_device);
+int exahype_cuda_time_loop_destroy(void* loop);
 
 #ifdef __cplusplus
 }

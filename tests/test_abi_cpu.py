@@ -32,7 +32,7 @@ def test_header_symbols_are_all_exported(lib):
 
 
 def test_version_and_registry(lib):
-    assert lib.exahype_cuda_version() == 1
+    assert lib.exahype_cuda_version() == 2
     inst = runtime.committed_instantiations()
     keys = {(i["model"], i["dim"], i["patch_size"], i["n_real"], i["n_aux"], i["dtype"]) for i in inst}
     # BASELINE.json configs C1..C4 and the shape of the reference's committed kernel
