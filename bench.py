@@ -286,9 +286,14 @@ def main():
     # --time-step host) dt is a host constant and lambda_max is only reduced -- the round-1 loop.
     peer_ok = reducer is None or reducer.backend == "peer"
     device_dt = args.time_step == "device" and peer_ok
-    loop = TimeLoop(dtype, reducer, args.cfl_dx, 0.01) if device_dt else None
-    if args.trace and reducer is not None and reducer.backend == "peer":
-        reducer.enable_trace(max(64, 2 * (args.steps + args.warmup) + 16))
+    tracer = reducer
+    if args.trace and world == 1 and device_dt:
+        from exahype_b200.dist import LocalPeerGroup
+        tracer = LocalPeerGroup(1)[0]            # one GPU: the loop's own one-rank exchange, with stamps
+    loop = TimeLoop(dtype, tracer if world == 1 else reducer, args.cfl_dx, 0.01) if device_dt else None
+    tracing = bool(args.trace) and tracer is not None and tracer.backend == "peer"
+    if tracing:
+        tracer.enable_trace(max(64, 2 * (args.steps + args.warmup) + 16))
     # host-dt mode: all-reduce in the patch kernel's own epilogue (blocking form, peer-memory backend)
     fused = (not device_dt) and reducer is not None and reducer.backend == "peer" and not args.no_fused
 
@@ -343,17 +348,17 @@ def main():
     barrier()
     launches = runtime.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if args.trace and reducer is not None and reducer.backend == "peer":
-        first_seq = loop.steps - args.steps + 1 if device_dt else 1
-        np.save(f"{args.trace}.rank{rank}.npy", reducer.read_trace(max(1, first_seq), args.steps))
+    if tracing:
+        first_seq = loop.steps - args.steps + 1 if device_dt else args.warmup + 1
+        np.save(f"{args.trace}.rank{rank}.npy", tracer.read_trace(max(1, first_seq), args.steps))
 
     # --- correctness of the multi-GPU path, outside the timed region
-    checks = verify_time_loop(torch, dist, upd, reducer, args, q_in, q_out, lam_patch, shard, world, rank) if device_dt else None
     if loop is not None:
-        loop.flush()
+        loop.flush()                              # the exchange still in flight belongs to the reducer, not to the loop
         torch.cuda.synchronize()
         hist = loop.history(loop.steps - 1, 2)
         lam_max.fill_(float(hist[1, 1]))          # the last step's global maximum
+    checks = verify_time_loop(torch, dist, upd, reducer, args, q_in, q_out, lam_patch, shard, world, rank) if device_dt else None
     if reducer is not None and not device_dt:
         # the collective is exact: the reduced scalar must equal torch.distributed's own MAX over the ranks' local values
         upd.step(q_in, q_out, 0.01, lam_patch, lam_max)

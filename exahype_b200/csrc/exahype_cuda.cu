@@ -255,7 +255,7 @@ int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, 
     err = cudaMemsetAsync(lambda_max, 0, elem_size(cfg->dtype), s);
     if (err != cudaSuccess) return cuda_fail(err, "cudaMemsetAsync(lambda_max)");
   }
-  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}};
+  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}, nullptr, nullptr, nullptr};
   err = exahype::peer_reducer_next_fused(r, &g.peer);
   if (err != cudaSuccess) return cuda_fail(err, "peer reducer not connected, or a time loop's exchange is still pending (flush it)");
   err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, &g);
@@ -278,7 +278,7 @@ int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_c
   }
   if (cells->n_patches == 0) return EXAHYPE_OK;
   if (!cells->q_in || !cells->q_out) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cells->q_in / cells->q_out must not be null");
-  const exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt, {}};
+  const exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt, {}, cells->cell_centre, cells->cell_size, cells->t};
   const int var = variant_of(cfg->flags);   // the CellData form exists for the shape's default kernel
   cudaError_t err = e->gather_launch[var](nullptr, nullptr, cells->n_patches, dt, cells->max_eigenvalue, lambda_max, s, &g);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (cell data)");
@@ -612,6 +612,8 @@ int exahype_cuda_time_loop_create(void** loop, int dtype, void* reducer, double 
   if (dtype != EXAHYPE_DTYPE_F64 && dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
   if (!(cfl_dx > 0.0) || history_capacity < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cfl_dx must be > 0 and history_capacity >= 0");
   if (int rc = reducer_failed(static_cast<exahype::PeerReducer*>(reducer))) return rc;
+  if (reducer && exahype::peer_reducer_pending(static_cast<exahype::PeerReducer*>(reducer)))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "the reducer still carries another time loop's exchange: flush that loop first");
   exahype::TimeLoop* l = nullptr;
   cudaError_t err = exahype::time_loop_create(&l, dtype, static_cast<exahype::PeerReducer*>(reducer), cfl_dx, dt0, history_capacity);
   if (err != cudaSuccess) return cuda_fail(err, "time_loop_create");
@@ -645,7 +647,7 @@ int exahype_cuda_fv_step_time_loop(const exahype_fv_config* cfg, void* loop, con
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_time_loop (launch info)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool in_kernel = info.fused_allreduce && n_patches > 0 && exahype::peer_reducer_world(r) <= 32;
-  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}};
+  exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}, nullptr, nullptr, nullptr};
   err = exahype::time_loop_next(l, in_kernel, &g.peer);
   if (err != cudaSuccess) return cuda_fail(err, "time loop: reducer not connected");
   if (n_patches > 0) {

@@ -597,6 +597,7 @@ struct Fv3dPairAutoConfig {
   static constexpr int NW0 = BY_SMEM < 8 ? BY_SMEM : 8;
   static constexpr int NW = NW0 >= 4 ? NW0 / 4 * 4 : (NW0 < 1 ? 1 : NW0);
   using type = Fv3dPairConfig<Phys, Upd, T, P, H, NW, R, DA, UH, false, 1>;
+  using gather_type = Fv3dPairConfig<Phys, Upd, T, P, H, NW, R, DA, UH, true, 1>;     // CellData form
 };
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 using Fv3dPairAuto = Fv3dPairLauncher<typename Fv3dPairAutoConfig<Phys, Upd, T, P, H, DA, UH>::type>;

@@ -27,6 +27,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "peer_mail.cuh"
 #include "physics.cuh"
 
@@ -56,6 +58,11 @@ struct FvGather {
   const T* const* q_in = nullptr;
   T* const* q_out = nullptr;
   const T* dt = nullptr;
+  // CellData::cellCentre / cellSize (dim values per patch) and CellData::t, for functors with the ExaHyPE2 solver
+  // signature flux(Q, x, h, t, dt, normal, F) (FvCellCtx below); null: centre 0, size 1, t 0
+  const T* cell_centre = nullptr;
+  const T* cell_size = nullptr;
+  const T* t = nullptr;
   // the step's time-step source and the all-reduce(max) of lambda_max (peer_mail.cuh): every kernel honours
   // peer.dt_in (device-resident dt); kernels whose launch info says fused_allreduce also run the exchange themselves
   // (peer.mode).  Rides along here because this struct already reaches every kernel.
@@ -81,6 +88,9 @@ struct FvGatherRaw {   // type-erased form crossing the registry's function poin
   void* const* q_out;
   const void* dt;
   FvPeerFuse peer;
+  const void* cell_centre = nullptr;
+  const void* cell_size = nullptr;
+  const void* t = nullptr;
 };
 template <typename T>
 inline FvGather<T> make_gather(const FvGatherRaw* raw) {
@@ -90,6 +100,9 @@ inline FvGather<T> make_gather(const FvGatherRaw* raw) {
     g.q_out = reinterpret_cast<T* const*>(raw->q_out);
     g.dt = static_cast<const T*>(raw->dt);
     g.peer = raw->peer;
+    g.cell_centre = static_cast<const T*>(raw->cell_centre);
+    g.cell_size = static_cast<const T*>(raw->cell_size);
+    g.t = static_cast<const T*>(raw->t);
   }
   return g;
 }
@@ -192,6 +205,52 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// Where and when a cell is: what ExaHyPE2's solver functions take next to Q -- flux(Q, x, h, t, dt, normal, F),
+// maxEigenvalue(Q, x, h, t, dt, normal) (reference "Unit test/correctness_test.cpp":90-99; call sites declared by
+// examples/kernel-generator.py:37-39).  Functor families that set `static constexpr bool NEEDS_CONTEXT = true` receive it
+// as an extra argument of flux<N> / eigen<N>; the committed Euler / shallow-water families do not depend on position or
+// time and never see it.  Definitions, in exactly this evaluation order (the C++ side of the parity test uses the same):
+//   h[d] = H[d] / patch_size                                   getVolumeSize(cellSize, patch_size)
+//   x[d] = (X[d] - 0.5 * H[d]) + (index[d] + 0.5) * h[d]       getVolumeCentre(cellCentre, cellSize, patch_size, {i, j(, k)})
+// with index[d] the haloed loop index the declaration passes (`{i, j}`), X / H the patch's cellCentre / cellSize.
+template <typename T, int DIM>
+struct FvCellCtx {
+  T x[DIM], h[DIM];   // volume centre and size
+  T X[DIM], H[DIM];   // patch centre and size
+  T t, dt;
+};
+template <class Phys, class = void> struct needs_context : std::false_type {};
+template <class Phys> struct needs_context<Phys, std::enable_if_t<Phys::NEEDS_CONTEXT>> : std::true_type {};
+
+template <class C>
+__device__ __forceinline__ FvCellCtx<typename C::T, C::DIM> cell_context(const FvGather<typename C::T>& gather,
+                                                                        long long patch, int cell, typename C::T dt) {
+  using T = typename C::T;
+  FvCellCtx<T, C::DIM> ctx;
+#pragma unroll
+  for (int d = 0; d < C::DIM; ++d) {
+    const int index = (cell / C::cell_stride(d)) % C::S;
+    ctx.X[d] = gather.cell_centre ? gather.cell_centre[patch * C::DIM + d] : T(0);
+    ctx.H[d] = gather.cell_size ? gather.cell_size[patch * C::DIM + d] : T(1);
+    ctx.h[d] = ctx.H[d] / T(C::P);
+    ctx.x[d] = (ctx.X[d] - T(0.5) * ctx.H[d]) + (T(index) + T(0.5)) * ctx.h[d];
+  }
+  ctx.t = gather.t ? gather.t[patch] : T(0);
+  ctx.dt = dt;
+  return ctx;
+}
+template <class C, int N, class Pr, class Ctx>
+__device__ __forceinline__ void ctx_flux(const typename C::T (&q)[C::NV], const Pr& pr, typename C::T (&F)[C::NR],
+                                         const Ctx& ctx) {
+  if constexpr (needs_context<typename C::Phys>::value) C::Phys::template flux<N, typename C::T>(q, pr, F, ctx);
+  else C::Phys::template flux<N, typename C::T>(q, pr, F);
+}
+template <class C, int N, class Pr, class Ctx>
+__device__ __forceinline__ typename C::T ctx_eigen(const typename C::T (&q)[C::NV], const Pr& pr, const Ctx& ctx) {
+  if constexpr (needs_context<typename C::Phys>::value) return C::Phys::template eigen<N, typename C::T>(q, pr, ctx);
+  else return C::Phys::template eigen<N, typename C::T>(q, pr);
+}
+
 template <class C>
 struct CellIndex {
   int g;             // patch within the tile
@@ -241,7 +300,8 @@ __device__ __forceinline__ void face_cell(int f, int& g, int& cell, int& slot) {
 template <class C, int N>
 __device__ __forceinline__ void eval_face(int f, int npatch, const typename C::T* __restrict__ qs,
                                           typename C::T* __restrict__ Fs, typename C::T* __restrict__ Ls,
-                                          typename C::T* __restrict__ Rs) {
+                                          typename C::T* __restrict__ Rs, const FvGather<typename C::T>& gather,
+                                          long long first_patch, typename C::T dt) {
   using T = typename C::T;
   using Phys = typename C::Phys;
   int g, cell, slot;
@@ -252,12 +312,15 @@ __device__ __forceinline__ void eval_face(int f, int npatch, const typename C::T
 #pragma unroll
   for (int v = 0; v < C::NV; ++v) q[v] = src[v];
   const auto pr = Phys::template prims<T>(q);
+  FvCellCtx<T, C::DIM> ctx;
+  if constexpr (needs_context<Phys>::value)
+    ctx = cell_context<C>(gather, first_patch + g, cell, gather.template step<C::GATHER>(dt, first_patch + g));
   T F[C::NR];
-  Phys::template flux<N, T>(q, pr, F);
+  ctx_flux<C, N>(q, pr, F, ctx);
   const int s = g * C::SLOTS + slot;
 #pragma unroll
   for (int v = 0; v < C::NR; ++v) Fs[(N * C::NR + v) * (C::G * C::SLOTS) + s] = F[v];
-  Ls[N * (C::G * C::SLOTS) + s] = Phys::template eigen<N, T>(q, pr);
+  Ls[N * (C::G * C::SLOTS) + s] = ctx_eigen<C, N>(q, pr, ctx);
   if (C::STASH_Q) {
 #pragma unroll
     for (int v = 0; v < C::DV; ++v) Rs[v * (C::G * C::NCELL) + g * C::NCELL + cell] = q[v];
@@ -353,29 +416,32 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
 #pragma unroll
         for (int v = 0; v < NV; ++v) q[r][v] = src[v];
         const auto pr = Phys::template prims<T>(q[r]);
+        FvCellCtx<T, DIM> ctx;
+        if constexpr (needs_context<Phys>::value)
+          ctx = cell_context<C>(gather, tile * G + ci.g, ci.cell, gather.template step<C::GATHER>(dt, tile * G + ci.g));
         T F[NR];
         {
-          Phys::template flux<0, T>(q[r], pr, F);
+          ctx_flux<C, 0>(q[r], pr, F, ctx);
           const int s = ci.g * C::SLOTS + ci.slot[0];
 #pragma unroll
           for (int v = 0; v < NR; ++v) Fs[(0 * NR + v) * FSTRIDE + s] = F[v];
-          lam[r][0] = Phys::template eigen<0, T>(q[r], pr);
+          lam[r][0] = ctx_eigen<C, 0>(q[r], pr, ctx);
           Ls[0 * FSTRIDE + s] = lam[r][0];
         }
         {
-          Phys::template flux<1, T>(q[r], pr, F);
+          ctx_flux<C, 1>(q[r], pr, F, ctx);
           const int s = ci.g * C::SLOTS + ci.slot[1];
 #pragma unroll
           for (int v = 0; v < NR; ++v) Fs[(1 * NR + v) * FSTRIDE + s] = F[v];
-          lam[r][1] = Phys::template eigen<1, T>(q[r], pr);
+          lam[r][1] = ctx_eigen<C, 1>(q[r], pr, ctx);
           Ls[1 * FSTRIDE + s] = lam[r][1];
         }
         if constexpr (DIM == 3) {
-          Phys::template flux<2, T>(q[r], pr, F);
+          ctx_flux<C, 2>(q[r], pr, F, ctx);
           const int s = ci.g * C::SLOTS + ci.slot[2];
 #pragma unroll
           for (int v = 0; v < NR; ++v) Fs[(2 * NR + v) * FSTRIDE + s] = F[v];
-          lam[r][2] = Phys::template eigen<2, T>(q[r], pr);
+          lam[r][2] = ctx_eigen<C, 2>(q[r], pr, ctx);
           Ls[2 * FSTRIDE + s] = lam[r][2];
         }
         if (C::STASH_Q) {
@@ -398,9 +464,9 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
     for (int f = tid; f < C::FACE_CELLS; f += NT) {
       const int n = f / C::FACES_PER_AXIS;
       const int ff = f - n * C::FACES_PER_AXIS;
-      if (n == 0) eval_face<C, 0>(ff, npatch, qs, Fs, Ls, Rs);
-      else if (n == 1) eval_face<C, 1>(ff, npatch, qs, Fs, Ls, Rs);
-      else if constexpr (DIM == 3) eval_face<C, 2>(ff, npatch, qs, Fs, Ls, Rs);
+      if (n == 0) eval_face<C, 0>(ff, npatch, qs, Fs, Ls, Rs, gather, tile * G, dt);
+      else if (n == 1) eval_face<C, 1>(ff, npatch, qs, Fs, Ls, Rs, gather, tile * G, dt);
+      else if constexpr (DIM == 3) eval_face<C, 2>(ff, npatch, qs, Fs, Ls, Rs, gather, tile * G, dt);
     }
     if (C::USE_TMA_STORE && tid == 0) tma_store_wait_read();   // previous tile's bulk store has drained `stage`
     __syncthreads();

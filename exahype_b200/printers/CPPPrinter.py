@@ -51,8 +51,19 @@ class _CxxExpr(StrPrinter):
             stride //= side
         if len(expr.indices) > 1 + k.dim and self._with_var and not self._address_of:
             terms.append(self._print(expr.indices[-1]))
-        ref = f"{self._p.qualified(name)}[{' + '.join(terms)}]"
+        if self._p.per_patch_member(name):
+            # member of an ExaHyPE2 CellData: one array per patch, `patchData.QIn[patch][...]` -- what the reference's
+            # CPPPrinter.parse (CPPPrinter.py:278-316) rewrites `patchData.QIn[stride*patch + ...]` into
+            ref = f"{self._p.qualified(name)}[{self._print(spatial[0])}][{' + '.join(terms[1:])}]"
+        else:
+            ref = f"{self._p.qualified(name)}[{' + '.join(terms)}]"
         return f"&{ref}" if self._address_of else ref
+
+    def _print_Symbol(self, expr):
+        name = str(expr)
+        if self._p.per_patch_member(name):      # `patchData.dt` -> `patchData.dt[patch]` (CPPPrinter.py:310-311)
+            return f"{self._p.qualified(name)}[{self._p.kernel().indexes[0]}]"
+        return self._p.qualified(name) if name in self._p.kernel().parents else super()._print_Symbol(expr)
 
     def _print_Function(self, expr):
         k = self._p.kernel()
@@ -115,6 +126,13 @@ class CPPPrinter(CodePrinter):
         if parent is None:
             return name
         return f"{parent}{name}" if parent.endswith(":") else f"{parent}.{name}"
+
+    def per_patch_member(self, name: str) -> bool:
+        """``name`` is a member of the first declared item and that item is an object, not an array (``in_type`` such as
+        ``::exahype2::CellData&``, reference ``examples/kernel-generator.py:8``): ExaHyPE2's ``CellData`` keeps one entry
+        per patch in every member -- ``QIn[patch]``, ``dt[patch]``, ``cellCentre[patch]``."""
+        k = self.kernel()
+        return bool(k.items) and k.parents.get(name) == k.items[0] and not k.input_types[0].rstrip().endswith("*")
 
     def _emit_raw(self, text: str):
         self._lines.append(text)

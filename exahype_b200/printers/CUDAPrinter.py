@@ -63,6 +63,15 @@ class RusanovProgram:
     dissipation: str              # device expression in (qc, q0, q_plus, q_minus, l0, l_plus, l_minus, dt)
     dissipation_all: bool         # False: variable 0 only, as the reference emits
     roles: List[str] = field(default_factory=list)   # one label per statement, for the listing
+    # what each argument of the flux / eigenvalue call is, in call order: 'Q' the cell's variables, 'F' the flux output,
+    # 'normal', and -- for ExaHyPE2's solver signature flux(Q, x, h, t, dt, normal, F) (kernel-generator.py:37-39) -- the
+    # cell context: 'x' volume centre, 'h' volume size, 'X' patch centre, 'H' patch size, 't', 'dt'
+    flux_args: List[str] = field(default_factory=lambda: ["Q", "normal", "F"])
+    eigen_args: List[str] = field(default_factory=lambda: ["Q", "normal"])
+
+    @property
+    def context(self) -> bool:
+        return any(a not in ("Q", "normal", "F") for a in self.flux_args + self.eigen_args)
 
 
 class _StatementPrinter(StrPrinter):
@@ -147,6 +156,38 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
     flux_calls, eig_calls, flux_upd, diss_upd = {}, {}, {}, {}
     normal_name, normals = None, {}
     pending_normal = None
+    # scalar members of the CellData object (kernel-generator.py:15-19: dt, t, cellCentre, cellSize with parent=Data)
+    members = {n for n in k.parents if isinstance(k.all_items.get(n), Symbol)}
+    flux_arg_tags, eigen_arg_tags = {}, {}
+
+    def classify(arg, is_flux_call: bool) -> str:
+        """What one argument of a flux / eigenvalue call is (see RusanovProgram.flux_args)."""
+        if isinstance(arg, Indexed):
+            b = base_of(arg)
+            if b == q_work:
+                return "Q"
+            if is_flux_call and any(b == d + sfx for d in k.directional_items for sfx in ("_x", "_y", "_z")):
+                return "F"
+            raise UnsupportedKernel(f"unexpected array argument {arg} in a flux / eigenvalue call")
+        if isinstance(arg, Symbol):
+            name = str(arg)
+            if name in k.directional_consts:
+                return "normal"
+            if name in members or name in k.inputs:
+                tag = {"dt": "dt", "t": "t", "cellCentre": "X", "cellSize": "H"}.get(name)
+                if tag:
+                    return tag
+            raise UnsupportedKernel(f"argument {arg} of a flux / eigenvalue call is not available inside the kernel")
+        if isinstance(arg, sympy.Function):
+            name = arg.func.__name__
+            # ExaHyPE2's exahype2::fv::getVolumeCentre(x, h, patch_size, index) / getVolumeSize(h, patch_size); without
+            # the index the declaration passes the patch centre (kernel-generator.py:39)
+            if name == "getVolumeCentre":
+                return "x" if any(isinstance(a, (sympy.Set, sympy.Tuple, set, frozenset)) for a in arg.args) else "X"
+            if name == "getVolumeSize":
+                return "h"
+        raise UnsupportedKernel(f"argument {arg} of a flux / eigenvalue call is not supported")
+
     for pos, (lhs, rhs, direction, struct) in enumerate(stmts):
         if pos == 0:
             roles.append("copy-in"); continue
@@ -159,11 +200,13 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
             if len(args) < 3 or base_of(args[0]) != q_work or not isinstance(args[-1], Indexed):
                 raise UnsupportedKernel(f"flux call {lhs} must be f({q_work}[c], {normal_name}, tmp[c])")
             flux_calls[direction] = (fn_name(lhs), base_of(args[-1]), pending_normal)
+            flux_arg_tags[direction] = [classify(a, True) for a in args]
             roles.append(f"flux axis {direction}"); continue
         if isinstance(lhs, Indexed) and fn_name(rhs):                      # L_d[c] = maxEigenvalue(Qc[c], normal)
             if base_of(rhs.args[0]) != q_work:
                 raise UnsupportedKernel(f"eigenvalue call {rhs} must read {q_work}[c]")
             eig_calls[direction] = (fn_name(rhs), base_of(lhs), pending_normal)
+            eigen_arg_tags[direction] = [classify(a, False) for a in rhs.args]
             roles.append(f"eigenvalue axis {direction}"); continue
         if isinstance(lhs, Indexed) and base_of(lhs) == q_work and isinstance(rhs, sympy.Expr):
             used = {base_of(a) for a in rhs.atoms(Indexed)}
@@ -193,10 +236,16 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
             raise UnsupportedKernel("the directional constant must be set ahead of each sweep")
     if [normals[d] for d in axes] != list(range(dim)):
         raise UnsupportedKernel("kernel template pairs sweep axis d with normal d-1 (reference Batched_stateless.py:17)")
+    for tags, what in ((flux_arg_tags, "flux"), (eigen_arg_tags, "eigenvalue")):
+        if any(tags[d] != tags[1] for d in axes):
+            raise UnsupportedKernel(f"the {what} call takes different arguments on different axes")
+        if tags[1].count("Q") != 1 or tags[1].count("normal") != 1 or (what == "flux" and tags[1][-1] != "F"):
+            raise UnsupportedKernel(f"the {what} call needs the cell's variables and the normal once each"
+                                    + (", and the flux output last" if what == "flux" else ""))
 
     # --- update expressions, printed per axis and required to be the same program on every axis -----------------
     max_candidates = [f for f in k.functions if f not in (next(iter(flux_fn)), next(iter(eigen_fn)))]
-    dt_names = [n for n in k.inputs]
+    dt_names = [n for n in k.inputs] + sorted(members)
 
     def names_for(rhs, d):
         names = {}
@@ -253,7 +302,8 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
     return RusanovProgram(q_in=q_in, q_work=q_work, flux_tmp=flux_tmp, eigen_tmp=eigen_tmp,
                           flux_fn=next(iter(flux_fn)), eigen_fn=next(iter(eigen_fn)), max_fn=max_fn,
                           normal=normal_name or "normal", normals=[normals[d] for d in axes], dt=dt,
-                          flux_update=flux_text, dissipation=diss_text, dissipation_all=dissipation_all, roles=roles)
+                          flux_update=flux_text, dissipation=diss_text, dissipation_all=dissipation_all, roles=roles,
+                          flux_args=flux_arg_tags[1], eigen_args=eigen_arg_tags[1])
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -361,6 +411,13 @@ class CUDAPrinter(CodePrinter):
         if template == "pair" and not can_pair:
             raise UnsupportedKernel("the warp-per-patch template serves 3-D patches of side 8 with one halo layer")
         small = k.n_real + k.n_aux <= 6
+        self.context = self.program.context and not self._all_builtin()
+        if self.context:
+            # functors that see the cell's position / time (ExaHyPE2's solver signature) are served by the thread-per-cell
+            # kernel, which knows every cell's index; the committed families ignore the context and keep every template
+            if template not in ("auto", "cell"):
+                raise UnsupportedKernel("functors taking x / h / t / dt run in the thread-per-cell template only")
+            can_pair = can_march = False
         if can_pair and (template == "pair" or (template == "auto" and small)):
             self.template = "pair"
         elif can_march and (template == "march" or (template == "auto" and small)):
@@ -400,6 +457,16 @@ class CUDAPrinter(CodePrinter):
         super().file(file_name, header_file_name)
 
     # ------------------------------------------------------------------ emission
+    def _all_builtin(self) -> bool:
+        fb, eb = self._body_of(self.program.flux_fn), self._body_of(self.program.eigen_fn)
+        return fb is not None and bool(fb.builtin) and (eb is None or eb.builtin == fb.builtin)
+
+    @staticmethod
+    def _call_args(tags: List[str]) -> str:
+        """Argument list of the user's device function, in the order the declaration calls it."""
+        return ", ".join({"Q": "q", "F": "F", "normal": "N", "x": "c.x", "h": "c.h", "X": "c.X", "H": "c.H", "t": "c.t",
+                          "dt": "c.dt"}[t] for t in tags)
+
     def _body_of(self, name: str) -> Optional[DeviceBody]:
         fn = self.kernel().all_items.get(name)
         body = getattr(fn, "device_body", None)
@@ -421,9 +488,16 @@ class CUDAPrinter(CodePrinter):
                 return f"using Physics = ::exahype::SwePhysics<{nr}, {na}>;   // csrc/physics.cuh\n"
             raise UnsupportedKernel(f"unknown builtin physics '{fam}'")
 
+        ctx = self.context
         out = [f"struct Physics {{\n  static constexpr int NR = {nr}, NA = {na}, NV = {nv};\n"
-               "  template <typename T> struct Prims {};\n"
+               + ("  static constexpr bool NEEDS_CONTEXT = true;   // functors take the cell's x / h / t / dt (FvCellCtx)\n" if ctx else "")
+               + "  template <typename T> struct Prims {};\n"
                "  template <typename T> static __device__ __forceinline__ Prims<T> prims(const T (&)[NV]) { return {}; }\n"]
+        ctx_tpl = ", class Ctx" if ctx else ""
+        # a body given as device source lives in `namespace user` (below); functions that come from the header passed to
+        # file() are global -- qualified either way, so that a declared name such as `flux` cannot hit the functor's members
+        scope = lambda body: "user::" if (body is not None and body.source) else "::"
+        ctx_arg = ", const Ctx& c" if ctx else ""
         q = sympy.symbols(f"q0:{nv}", real=True)
         prn = _DevicePrinter()
 
@@ -434,32 +508,37 @@ class CUDAPrinter(CodePrinter):
             return text
 
         # flux
-        out.append("  template <int N, typename T>\n"
-                   "  static __device__ __forceinline__ void flux(const T (&q)[NV], const Prims<T>&, T (&F)[NR]) {\n")
+        out.append(f"  template <int N, typename T{ctx_tpl}>\n"
+                   f"  static __device__ __forceinline__ void flux(const T (&q)[NV], const Prims<T>&, T (&F)[NR]{ctx_arg}) {{\n")
+        if ctx and ((fb is not None and fb.expressions) or (eb is not None and eb.expressions)):
+            raise UnsupportedKernel("functors taking x / h / t / dt need a device-source body (DeviceBody(source=...))")
         if fb is not None and fb.expressions:
             for n in range(dim):
                 comps = list(fb.expressions(list(q), n))
                 if len(comps) != nr:
                     raise ValueError(f"{p.flux_fn}: expected {nr} flux components, got {len(comps)}")
                 out.append(f"    if (N == {n}) {{\n" + "".join(f"      F[{v}] = {lower(c)};\n" for v, c in enumerate(comps)) + "    }\n")
-        else:   # user's device function with the reference signature: void Flux(const T* Q, int normal, T* F)
-            out.append(f"    {p.flux_fn}(q, N, F);\n")
+        else:   # user's device function with the declared signature: void Flux(const T* Q, int normal, T* F) in the
+            # reference's Functions.h:2, flux(Q, x, h, t, dt, normal, F) for an ExaHyPE2 solver
+            out.append(f"    {scope(fb)}{p.flux_fn}({self._call_args(p.flux_args)});\n")
         out.append("  }\n")
         # eigenvalue
-        out.append("  template <int N, typename T>\n"
-                   "  static __device__ __forceinline__ T eigen(const T (&q)[NV], const Prims<T>&) {\n")
+        out.append(f"  template <int N, typename T{ctx_tpl}>\n"
+                   f"  static __device__ __forceinline__ T eigen(const T (&q)[NV], const Prims<T>&{ctx_arg}) {{\n")
         if eb is not None and eb.expressions:
             for n in range(dim):
                 out.append(f"    if (N == {n}) return {lower(eb.expressions(list(q), n))};\n")
             out.append("    return T(0);\n")
         else:
-            out.append(f"    return {p.eigen_fn}(q, N);\n")
+            out.append(f"    return {scope(eb)}{p.eigen_fn}({self._call_args(p.eigen_args)});\n")
         out.append("  }\n};\n")
         pre = ""
         for b in (fb, eb):
             if b is not None and b.source and b.source not in pre:
                 pre += b.source.rstrip() + "\n\n"
-        return pre + "".join(out)
+        # the user's functions live in their own namespace: a declared name such as `flux` must not collide with the
+        # functor's members
+        return "namespace user {\n" + pre + "}  // namespace user\n\n" + "".join(out)
 
     def _emit(self) -> str:
         k, p = self.kernel(), self.program
@@ -469,23 +548,28 @@ class CUDAPrinter(CodePrinter):
         T = self.ctype
         fname = self.functionName()
         b = lambda x: str(bool(x)).lower()
+        geo = f"Physics, Update, {T}, {k.patch_size}, {k.halo_size}"
         if self.template == "cell":
             header = "fv_patch_kernel.cuh"
-            launcher = lambda da, uh: (f"::exahype::FvLauncher<::exahype::FvKernelConfig<Physics, Update, {T}, {k.dim}, "
-                                       f"{k.patch_size}, {k.halo_size}, {self.patches_per_tile}, {self.threads}, "
-                                       f"{self.min_ctas}, {b(da)}, {b(uh)}>>")
+            launcher = lambda da, uh, gather=False: (
+                f"::exahype::FvLauncher<::exahype::FvKernelConfig<Physics, Update, {T}, {k.dim}, "
+                f"{k.patch_size}, {k.halo_size}, {self.patches_per_tile}, {self.threads}, "
+                f"{self.min_ctas}, {b(da)}, {b(uh)}, {b(gather)}>>")
         elif k.dim == 2:
             header = "fv2d_march_kernel.cuh"
-            launcher = lambda da, uh: (f"::exahype::Fv2dMarchAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
-                                       f"{b(da)}, {b(uh)}>")
+            launcher = lambda da, uh, gather=False: (
+                f"::exahype::Fv2dMarchGather<{geo}, {b(da)}, {b(uh)}>" if gather else
+                f"::exahype::Fv2dMarchAuto<{geo}, {b(da)}, {b(uh)}>")
         elif self.template == "pair":
             header = "fv3d_pair_kernel.cuh"
-            launcher = lambda da, uh: (f"::exahype::Fv3dPairAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
-                                       f"{b(da)}, {b(uh)}>")
+            launcher = lambda da, uh, gather=False: (
+                f"::exahype::Fv3dPairLauncher<typename ::exahype::Fv3dPairAutoConfig<{geo}, {b(da)}, {b(uh)}>::gather_type>"
+                if gather else f"::exahype::Fv3dPairAuto<{geo}, {b(da)}, {b(uh)}>")
         else:
             header = "fv3d_march_kernel.cuh"
-            launcher = lambda da, uh: (f"::exahype::Fv3dMarchAuto<Physics, Update, {T}, {k.patch_size}, {k.halo_size}, "
-                                       f"{b(da)}, {b(uh)}>")
+            launcher = lambda da, uh, gather=False: (
+                f"::exahype::Fv3dMarchLauncher<typename ::exahype::Fv3dMarchAutoConfig<{geo}, {b(da)}, {b(uh)}>::gather_type>"
+                if gather else f"::exahype::Fv3dMarchAuto<{geo}, {b(da)}, {b(uh)}>")
         da = self.dissipation_all
         parts = []
         if self.header_file_name:
@@ -496,7 +580,7 @@ class CUDAPrinter(CodePrinter):
             f"dtype={self.dtype}; dissipation={'all' if da else 'var0'}; kernel template: {header}\n"
             "// Statement list (KernelBuilder) and where each statement went in the fused kernel:\n"
             + "".join(self._statements) +
-            f"#include <stdint.h>\n#include <cuda_runtime.h>\n#include \"{header}\"\n\nnamespace {{\n\n")
+            f"#include <stdint.h>\n#include <cuda_runtime.h>\n#include \"{header}\"\n#include \"exahype_cuda.h\"\n\nnamespace {{\n\n")
         parts.append(self._physics())
         parts.append(
             "\n// update statements in the evaluation order of the declaration (SymPy str order == reference C++ order)\n"
@@ -517,39 +601,92 @@ class CUDAPrinter(CodePrinter):
             f"  if (lambda_max && !(flags & 4u) && cudaMemsetAsync(lambda_max, 0, sizeof({T}), s) != cudaSuccess) return -3;\n"
             "  if (n_patches <= 0) return n_patches < 0 ? -1 : 0;\n"
             "  if (!q_in || !q_out || ((uintptr_t)q_in & 15) || ((uintptr_t)q_out & 15)) return -1;\n"
+            "  if ((flags & 2u) && q_in == q_out) return -1;   // un-haloed output cannot alias the haloed input\n"
             "  cudaError_t err = (flags & 2u)\n"
             f"      ? {launcher(da, True)}::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s)\n"
             f"      : {launcher(da, False)}::launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s);\n"
+            "  return err == cudaSuccess ? 0 : -3;\n}\n\n"
+            "// The ExaHyPE2 CellData form of the same step (include/exahype_cuda.h exahype_cell_data: per-patch QIn / QOut\n"
+            "// pointers, dt, t, cellCentre, cellSize, maxEigenvalue -- reference examples/kernel-generator.py:8-19).\n"
+            f'extern "C" __attribute__((visibility("default")))\n'
+            f"int {fname}_cell_data(const exahype_cell_data* cells, double dt, void* lambda_max, unsigned flags, void* stream) {{\n"
+            "  cudaStream_t s = static_cast<cudaStream_t>(stream);\n"
+            "  if (!cells || cells->n_patches < 0) return -1;\n"
+            f"  if (lambda_max && !(flags & 4u) && cudaMemsetAsync(lambda_max, 0, sizeof({T}), s) != cudaSuccess) return -3;\n"
+            "  if (cells->n_patches == 0) return 0;\n"
+            "  if (!cells->q_in || !cells->q_out) return -1;\n"
+            "  const ::exahype::FvGatherRaw g = {cells->q_in, cells->q_out, cells->dt, {}, cells->cell_centre, cells->cell_size, cells->t};\n"
+            "  cudaError_t err = (flags & 2u)\n"
+            f"      ? {launcher(da, True, True)}::launch(nullptr, nullptr, cells->n_patches, dt, cells->max_eigenvalue, lambda_max, s, &g)\n"
+            f"      : {launcher(da, False, True)}::launch(nullptr, nullptr, cells->n_patches, dt, cells->max_eigenvalue, lambda_max, s, &g);\n"
             "  return err == cudaSuccess ? 0 : -3;\n}\n")
         return "".join(parts)
 
     # ------------------------------------------------------------------ compile + bind
+    @staticmethod
+    def cache_directory() -> str:
+        """Per-user, mode 0700: ``$EXAHYPE_B200_CACHE`` or ``~/.cache/exahype_b200/generated``."""
+        d = os.environ.get("EXAHYPE_B200_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "exahype_b200", "generated")
+        os.makedirs(d, mode=0o700, exist_ok=True)
+        return d
+
+    def build_tag(self, extra=()) -> str:
+        """Key of a built unit: the generated code AND everything else that decides the binary -- the kernel templates and
+        the ABI header it includes, the nvcc flags, the compiler version."""
+        from .. import build as _b
+        h = hashlib.sha256()
+        h.update(self.code.encode())
+        for root in (CSRC, INCLUDE):
+            for name in sorted(os.listdir(root)):
+                if name.endswith((".cuh", ".h")):
+                    with open(os.path.join(root, name), "rb") as f:
+                        h.update(name.encode() + b"\0" + f.read())
+        h.update(" ".join(_b.NVCC_FLAGS + list(extra)).encode())
+        try:
+            h.update(subprocess.run([_b.nvcc(), "--version"], capture_output=True, text=True).stdout.encode())
+        except Exception:
+            pass
+        return h.hexdigest()[:20]
+
     def build(self, directory: Optional[str] = None, include_dirs=(), verbose: bool = False) -> "GeneratedKernel":
         """nvcc the unit for sm_100a into a shared library (cross-compiles without a GPU) and bind it."""
         from .. import build as _b
-        directory = directory or os.path.join(tempfile.gettempdir(), "exahype_b200_generated")
+        directory = directory or self.cache_directory()
         os.makedirs(directory, exist_ok=True)
-        tag = hashlib.sha1(self.code.encode()).hexdigest()[:16]
-        src = os.path.join(directory, f"{self.functionName()}_{tag}.cu")
+        tag = self.build_tag(include_dirs)
         lib = os.path.join(directory, f"lib{self.functionName()}_{tag}.so")
+        if os.path.exists(lib) and hasattr(os, "getuid") and os.stat(lib).st_uid != os.getuid():
+            raise RuntimeError(f"{lib} exists but belongs to another user: refusing to load it")
         if not os.path.exists(lib):
-            with open(src, "w") as f:
+            # private names until the atomic rename: ranks of one job build the same unit at the same time
+            fd, src = tempfile.mkstemp(prefix=f"{self.functionName()}_{tag}_", suffix=".cu", dir=directory)
+            with os.fdopen(fd, "w") as f:
                 f.write(self.code)
+            tmp = src[:-3] + ".so.tmp"
             cmd = [_b.nvcc()] + _b.NVCC_FLAGS + _b._host_compiler_args() + ["-I", CSRC, "-I", INCLUDE]
             for d in include_dirs:
                 cmd += ["-I", d]
-            cmd += ["-shared", src, "-o", lib + ".tmp", "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+            cmd += ["-shared", src, "-o", tmp, "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode:
-                raise RuntimeError(f"nvcc failed on the generated kernel:\n{r.stderr}")
-            os.replace(lib + ".tmp", lib)
+                raise RuntimeError(f"nvcc failed on the generated kernel ({src}):\n{r.stderr}")
+            os.replace(tmp, lib)
+            os.replace(src, os.path.join(directory, f"{self.functionName()}_{tag}.cu"))
         return GeneratedKernel(self, lib)
 
 
+class _CellData(ctypes.Structure):
+    """``exahype_cell_data`` of include/exahype_cuda.h."""
+    _fields_ = [("n_patches", ctypes.c_int64), ("q_in", ctypes.c_void_p), ("q_out", ctypes.c_void_p),
+                ("dt", ctypes.c_void_p), ("max_eigenvalue", ctypes.c_void_p), ("cell_centre", ctypes.c_void_p),
+                ("cell_size", ctypes.c_void_p), ("t", ctypes.c_void_p)]
+
+
 class GeneratedKernel:
-    """A compiled ``CUDAPrinter`` unit: same ``step`` call as :class:`exahype_b200.runtime.PatchUpdate`."""
+    """A compiled ``CUDAPrinter`` unit: same ``step`` / ``step_cell_data`` calls as
+    :class:`exahype_b200.runtime.PatchUpdate`, with the same argument checks."""
 
     def __init__(self, printer: CUDAPrinter, lib_path: str):
         k = printer.kernel()
@@ -561,6 +698,9 @@ class GeneratedKernel:
         vp = ctypes.c_void_p
         self._fn.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_double, vp, vp, ctypes.c_uint, vp]
         self._fn.restype = ctypes.c_int
+        self._fn_cells = getattr(self._lib, printer.functionName() + "_cell_data")
+        self._fn_cells.argtypes = [ctypes.POINTER(_CellData), ctypes.c_double, vp, ctypes.c_uint, vp]
+        self._fn_cells.restype = ctypes.c_int
 
     def in_shape(self, n):
         return (n,) + (self.patch_size + 2 * self.halo_size,) * self.dim + (self.n_real + self.n_aux,)
@@ -568,15 +708,38 @@ class GeneratedKernel:
     def out_shape(self, n, unhaloed=False):
         return (n,) + (self.patch_size,) * self.dim + (self.n_real + self.n_aux,) if unhaloed else self.in_shape(n)
 
+    def _tdt(self):
+        import torch
+        return torch.float64 if self.dtype == "f64" else torch.float32
+
     def step(self, q_in, q_out=None, dt: float = 0.0, lambda_patch=None, lambda_max=None, stream=None,
              unhaloed: bool = False, accumulate_lambda: bool = False):
         import torch
+        tdt = self._tdt()
         if q_out is None:
+            if unhaloed:
+                raise ValueError("un-haloed output needs an explicit q_out")
             q_out = q_in
         per = (self.patch_size + 2 * self.halo_size) ** self.dim * (self.n_real + self.n_aux)
-        if q_in.numel() % per or not q_in.is_cuda or not q_in.is_contiguous():
-            raise ValueError("q_in must be a contiguous CUDA tensor holding whole patches")
+        if not q_in.is_cuda or q_in.numel() % per:
+            raise ValueError("q_in must be a CUDA tensor holding whole patches")
+        for name, t in (("q_in", q_in), ("q_out", q_out), ("lambda_patch", lambda_patch), ("lambda_max", lambda_max)):
+            if t is None:
+                continue
+            if t.dtype != tdt or not t.is_contiguous() or not t.is_cuda or t.device != q_in.device:
+                raise ValueError(f"{name} must be a contiguous {tdt} CUDA tensor on {q_in.device}")
         n = q_in.numel() // per
+        want = 1
+        for d in self.out_shape(n, unhaloed):
+            want *= d
+        if q_out is not q_in and q_out.numel() != want:
+            raise ValueError(f"q_out must hold {self.out_shape(n, unhaloed)}")
+        if unhaloed and q_out.data_ptr() == q_in.data_ptr():
+            raise ValueError("un-haloed output cannot alias the haloed input")
+        if lambda_patch is not None and lambda_patch.numel() < n:
+            raise ValueError("lambda_patch must hold one value per patch")
+        if lambda_max is not None and lambda_max.numel() < 1:
+            raise ValueError("lambda_max must hold one value")
         if stream is None:
             stream = torch.cuda.current_stream(q_in.device).cuda_stream
         flags = (2 if unhaloed else 0) | (4 if accumulate_lambda else 0)
@@ -587,3 +750,28 @@ class GeneratedKernel:
         if rc:
             raise RuntimeError(f"generated kernel failed with code {rc}")
         return q_out
+
+    def step_cell_data(self, q_in_ptrs, q_out_ptrs, dt: float = 0.0, dt_patch=None, max_eigenvalue=None, lambda_max=None,
+                       cell_centre=None, cell_size=None, t_patch=None, unhaloed: bool = False, stream=None):
+        """The ``CellData`` form: int64 CUDA tensors of per-patch device pointers, optional per-patch ``dt`` / ``t``
+        (``[n]``) and ``cellCentre`` / ``cellSize`` (``[n, dim]``) of this kernel's dtype, per-patch ``maxEigenvalue`` out."""
+        import torch
+        tdt = self._tdt()
+        n = int(q_in_ptrs.numel())
+        for name, ten, want, count in (("q_in_ptrs", q_in_ptrs, torch.int64, n), ("q_out_ptrs", q_out_ptrs, torch.int64, n),
+                                       ("dt_patch", dt_patch, tdt, n), ("max_eigenvalue", max_eigenvalue, tdt, n),
+                                       ("lambda_max", lambda_max, tdt, 1), ("cell_centre", cell_centre, tdt, n * self.dim),
+                                       ("cell_size", cell_size, tdt, n * self.dim), ("t_patch", t_patch, tdt, n)):
+            if ten is None:
+                continue
+            if not ten.is_cuda or not ten.is_contiguous() or ten.dtype != want or ten.numel() < count:
+                raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {want} with at least {count} values")
+        if stream is None:
+            stream = torch.cuda.current_stream(q_in_ptrs.device).cuda_stream
+        ptr = lambda x: x.data_ptr() if x is not None else None
+        cells = _CellData(n, q_in_ptrs.data_ptr(), q_out_ptrs.data_ptr(), ptr(dt_patch), ptr(max_eigenvalue),
+                          ptr(cell_centre), ptr(cell_size), ptr(t_patch))
+        with torch.cuda.device(q_in_ptrs.device):
+            rc = self._fn_cells(ctypes.byref(cells), float(dt), ptr(lambda_max), 2 if unhaloed else 0, stream)
+        if rc:
+            raise RuntimeError(f"generated kernel (cell data) failed with code {rc}")

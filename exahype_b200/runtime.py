@@ -47,7 +47,8 @@ class FvConfig(ctypes.Structure):
 class CellData(ctypes.Structure):
     """``exahype_cell_data`` of include/exahype_cuda.h (ExaHyPE2's ``CellData``: per-patch pointers and time steps)."""
     _fields_ = [("n_patches", ctypes.c_int64), ("q_in", ctypes.c_void_p), ("q_out", ctypes.c_void_p),
-                ("dt", ctypes.c_void_p), ("max_eigenvalue", ctypes.c_void_p)]
+                ("dt", ctypes.c_void_p), ("max_eigenvalue", ctypes.c_void_p), ("cell_centre", ctypes.c_void_p),
+                ("cell_size", ctypes.c_void_p), ("t", ctypes.c_void_p)]
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -333,7 +334,7 @@ class PatchUpdate:
             stream = torch.cuda.current_stream(q_in_ptrs.device).cuda_stream
         cells = CellData(n, q_in_ptrs.data_ptr(), q_out_ptrs.data_ptr(),
                          dt_patch.data_ptr() if dt_patch is not None else None,
-                         max_eigenvalue.data_ptr() if max_eigenvalue is not None else None)
+                         max_eigenvalue.data_ptr() if max_eigenvalue is not None else None, None, None, None)
         c = self.config()
         with torch.cuda.device(q_in_ptrs.device):
             check(self._lib.exahype_cuda_fv_step_cell_data(

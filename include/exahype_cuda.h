@@ -103,6 +103,12 @@ int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q
  *                   with EXAHYPE_FLAG_OUTPUT_UNHALOED each points to P^dim * (n_real+n_aux) values (CellData::QOut)
  *   dt              device array of n_patches time steps of cfg->dtype (CellData::dt); null: the scalar `dt` argument
  *   max_eigenvalue  device array of n_patches, nullable (CellData::maxEigenvalue): as lambda_patch of exahype_cuda_fv_step
+ *   cell_centre     device array of n_patches * dim values (CellData::cellCentre), nullable: 0
+ *   cell_size       device array of n_patches * dim values (CellData::cellSize), nullable: 1
+ *   t               device array of n_patches time stamps (CellData::t), nullable: 0
+ * cell_centre / cell_size / t reach functors declared with ExaHyPE2's solver signature flux(Q, x, h, t, dt, normal, F)
+ * (kernel-generator.py:37-39; units generated by CUDAPrinter from such a declaration); the committed Euler and
+ * shallow-water families do not depend on position or time and ignore them.
  */
 typedef struct {
   int64_t n_patches;
@@ -110,6 +116,9 @@ typedef struct {
   void* const* q_out;
   const void* dt;
   void* max_eigenvalue;
+  const void* cell_centre;
+  const void* cell_size;
+  const void* t;
 } exahype_cell_data;
 
 int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_cell_data* cells, double dt,

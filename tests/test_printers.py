@@ -78,7 +78,7 @@ def test_cuda_printer_recognises_the_program():
     assert "Fv3dMarchAuto<Physics, Update, double, 4, 1" in CUDAPrinter(
         batched_stateless(KernelBuilder, 3, 4, 1, 5, 0), model="euler").code
     cell = CUDAPrinter(k, model="euler", template="cell")
-    assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true>" in cell.code
+    assert "FvKernelConfig<Physics, Update, double, 3, 8, 1, 1, 512, 1, false, true, false>" in cell.code
     assert "Fv2dMarchAuto<Physics, Update, double, 16, 1, false, false>" in CUDAPrinter(
         batched_stateless(KernelBuilder, 2, 16, 1, 4, 0), model="euler").code
     assert "FvKernelConfig" in CUDAPrinter(batched_stateless(KernelBuilder, 2, 3, 1, 4, 0), model="euler").code

@@ -73,8 +73,11 @@ def test_kernel_generator_script_runs_verbatim(tmp_path):
     _run(source, tmp_path)
     code = (tmp_path / "generated_kernel.cpp").read_text()
     assert "void time_step(::exahype2::CellData& patchData, ::tarch::timing::Measurement& timingComputeKernel)" in code
-    assert "patchData.QIn[144*patch + 24*i + 4*j + var] = patchData.QOut[144*patch + 24*i + 4*j + var];" in code
-    assert "instanceOfFVRusanovSolver.flux(&patchData.QIn[" in code
+    # members of the CellData object hold one entry per patch (what the reference's CPPPrinter.parse, :278-316, is after)
+    assert "patchData.QIn[patch][24*i + 4*j + var] = patchData.QOut[patch][24*i + 4*j + var];" in code
+    assert "instanceOfFVRusanovSolver.flux(&patchData.QIn[patch][24*i + 4*j], exahype2::fv::getVolumeCentre(" \
+           "patchData.cellCentre[patch], patchData.cellSize[patch], patch_size, {i, j})" in code
+    assert "patchData.t[patch], patchData.dt[patch], normal, &tmp_flx_x[" in code and "0.5*patchData.dt[patch]*(" in code
     assert "for (int i = 0; i < 6; i++) {\n\t\t\tfor (int j = 1; j < 5; j++) {" in code      # axis 0: full along i
     assert "for (int i = 1; i < 5; i++) {\n\t\t\tfor (int j = 0; j < 6; j++) {" in code      # axis 1: full along j
     assert "&&" not in code and "= None" not in code and "patch - 1" not in code             # the HEAD defects
