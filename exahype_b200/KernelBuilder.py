@@ -192,12 +192,17 @@ class KernelBuilder:
                 if self.item_struct.get(name, 2) != 0:
                     full.append(term)
                 continue
-            if level == direction and offset != 0:
-                term += f"{offset:+d}"
-            elif term == "patch":
+            if term == "patch":
                 term += f"-{shift_patch}" if shift_patch else ""
-            elif shift_spatial:
-                term += f"-{shift_spatial}"
+            elif self.reference_head_quirks:
+                # HEAD drops the shift on the sweep axis whenever the access is offset (KernelBuilder.py:204-218)
+                if level == direction and offset != 0:
+                    term += f"{offset:+d}"
+                elif shift_spatial:
+                    term += f"-{shift_spatial}"
+            else:
+                total = (offset if level == direction else 0) - shift_spatial
+                term += f"{total:+d}" if total else ""
             full.append(term)
         return f"{name}[{','.join(full)}]"
 

@@ -20,7 +20,10 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexahype_cuda.so")
 
-SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "synthetic.cu", "peer_reduce.cu"]
+SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "inst_fast.cu", "synthetic.cu", "peer_reduce.cu"]
+# per-source flags appended after NVCC_FLAGS: the opt-in fast-arithmetic instantiations are the one unit whose
+# multiply-add pairs may contract (every kernel in it carries the ArithFast policy type, csrc/physics.cuh)
+SOURCE_FLAGS = {"inst_fast.cu": ["-fmad=true"]}
 HEADERS = ["fv_patch_kernel.cuh", "peer_mail.cuh", "fv3d_march_kernel.cuh", "fv3d_pair_kernel.cuh", "fv2d_march_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-lineinfo",
@@ -69,7 +72,8 @@ def _build(force: bool, verbose: bool, extra_flags) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc()] + NVCC_FLAGS + _host_compiler_args() + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        flags = [f for f in NVCC_FLAGS if not (src in SOURCE_FLAGS and f.startswith("-fmad"))] + SOURCE_FLAGS.get(src, [])
+        cmd = [nvcc()] + flags + _host_compiler_args() + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -100,18 +100,24 @@ int validate(const exahype_fv_config* cfg) {
   if (cfg->dtype != EXAHYPE_DTYPE_F64 && cfg->dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
   if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
   if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE |
-                     EXAHYPE_FLAG_KERNEL_CELL))
+                     EXAHYPE_FLAG_KERNEL_CELL | EXAHYPE_FLAG_FAST_ARITHMETIC))
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown flag bits 0x%x", cfg->flags);
   return EXAHYPE_OK;
 }
 
+bool same_shape(const exahype_fv_config& c, const exahype_fv_config* cfg) {
+  return c.model == cfg->model && c.dtype == cfg->dtype && c.dim == cfg->dim && c.patch_size == cfg->patch_size &&
+         c.halo == cfg->halo && c.n_real == cfg->n_real && c.n_aux == cfg->n_aux;
+}
+
 const exahype::FvEntry* find(const exahype_fv_config* cfg) {
-  for (const exahype::FvEntry& e : registry()) {
-    const exahype_fv_config& c = e.cfg;
-    if (c.model == cfg->model && c.dtype == cfg->dtype && c.dim == cfg->dim && c.patch_size == cfg->patch_size &&
-        c.halo == cfg->halo && c.n_real == cfg->n_real && c.n_aux == cfg->n_aux)
-      return &e;
+  if (cfg->flags & EXAHYPE_FLAG_FAST_ARITHMETIC) {      // a permission, not a demand: shapes without a fast build keep
+    const exahype::FvEntryList fast = exahype::fast_entries();   // the reference arithmetic
+    for (int i = 0; i < fast.count; ++i)
+      if (same_shape(fast.entries[i].cfg, cfg) && !(cfg->flags & EXAHYPE_FLAG_KERNEL_CELL)) return &fast.entries[i];
   }
+  for (const exahype::FvEntry& e : registry())
+    if (same_shape(e.cfg, cfg)) return &e;
   return nullptr;
 }
 

@@ -23,6 +23,8 @@
 // AoS plane has a cell stride of 5 doubles, scratch rows are pitched 10, the staging buffer is two padded segments.
 #pragma once
 
+#include <cstdlib>
+
 #include "fv3d_march_kernel.cuh"
 
 namespace exahype {
@@ -449,6 +451,10 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   ps.full = reinterpret_cast<unsigned long long*>(ws + C::OFF_BAR);   // [R]
   ps.lane = lane;
 
+  // Programmatic dependent launch (time-loop launches carry the attribute, see the launcher): let the NEXT launch of the
+  // stream be scheduled right away -- its CTAs take an SM as soon as one of ours leaves and run their start-up (barrier
+  // set-up, lane geometry) while the rest of this grid finishes -- ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (lane == 0) {
     for (int s = 0; s < R; ++s) mbar_init(&ps.full[s], 1);
     fence_mbar_init();
@@ -467,7 +473,6 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   ps.p_ip = ps.p_slot = 0;
   ps.p_src = q_in;
   if (my_patches > 0) ps.p_src = gather.template in<C::GATHER>(q_in, w_index, C::PATCH_ELEMS);
-  for (int s = 0; s < R; ++s) ps.issue_next_load(gather);
 
   // lane -> (row pair jp, column k): a half-warp holds the pairs {0, 2} or {1, 3}
   PairLane<C> ln;
@@ -506,6 +511,10 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
     }
   T lam_local = T(0), warp_lam = T(0);
 
+  // ... and touch nothing the PREVIOUS launch may still be writing (its output may be this launch's input, its last warp
+  // publishes the time step) before that grid has completed and flushed.  No-ops without the launch attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int s = 0; s < R; ++s) ps.issue_next_load(gather);
   const bool first_warp = (w_index == 0);
   if (first_warp && lane == 0 && gather.peer.mode == FV_PEER_LOOP) peer_trace(gather.peer, gather.peer.seq, FV_TRACE_KERNEL_BEGIN);
   // Device-resident time step (peer_mail.cuh): the ring is requested, the lane geometry is set up; a wait for the
@@ -536,6 +545,15 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   // (blocking), or only publishes it for the next launch's warps to consume (time loop)
   if (gather.peer.mode == FV_PEER_BLOCKING || gather.peer.mode == FV_PEER_LOOP)
     fused_allreduce_max<T, Bits>(gather.peer, lambda_max, lane, gridDim.x * (unsigned)C::NW);
+}
+
+// EXAHYPE_PDL=0 in the environment turns programmatic dependent launch off (A/B measurements)
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EXAHYPE_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 template <class C>
@@ -577,9 +595,27 @@ struct Fv3dPairLauncher {
     FvLaunchInfo info;
     cudaError_t err = prepare(&info, n_patches);
     if (err != cudaSuccess) return err;
+    const FvGather<T> g = make_gather<T>(gather);
+    if (g.peer.mode == FV_PEER_LOOP && pdl_enabled()) {
+      // steps of a device-resident time loop follow each other with nothing in between (no memset, no second kernel):
+      // programmatic stream serialization overlaps this launch's scheduling and start-up with the previous step's tail
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)info.grid);
+      cfg.blockDim = dim3((unsigned)info.block);
+      cfg.dynamicSmemBytes = (size_t)info.smem_bytes;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, fv3d_pair_kernel<C>, static_cast<const T*>(q_in), static_cast<T*>(q_out),
+                                (long long)n_patches, static_cast<T>(dt), static_cast<T*>(lambda_patch),
+                                static_cast<T*>(lambda_max), g);
+    }
     fv3d_pair_kernel<C><<<info.grid, info.block, info.smem_bytes, stream>>>(
         static_cast<const T*>(q_in), static_cast<T*>(q_out), n_patches, static_cast<T>(dt),
-        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), make_gather<T>(gather));
+        static_cast<T*>(lambda_patch), static_cast<T*>(lambda_max), g);
     return cudaGetLastError();
   }
 };

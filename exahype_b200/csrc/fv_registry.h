@@ -36,6 +36,7 @@ struct FvEntryList {
 FvEntryList euler2d_entries();
 FvEntryList euler3d_entries();
 FvEntryList swe2d_entries();
+FvEntryList fast_entries();     // inst_fast.cu: ArithFast + -fmad=true, looked up under EXAHYPE_FLAG_FAST_ARITHMETIC
 
 // A committed shape is described by up to three launcher families, each a template over (DISSIPATION_ALL, UNHALOED):
 // Main (default kernel, dense batch), Gather (same kernel, CellData form) and Alt (second kernel, or NoKernel).

@@ -27,6 +27,7 @@ FLAG_DISSIPATION_ALL = 1 << 0
 FLAG_OUTPUT_UNHALOED = 1 << 1
 FLAG_LAMBDA_ACCUMULATE = 1 << 2
 FLAG_KERNEL_CELL = 1 << 3
+FLAG_FAST_ARITHMETIC = 1 << 4
 
 ERR_NAMES = {-1: "INVALID_ARGUMENT", -2: "NO_INSTANTIATION", -3: "CUDA", -4: "NCCL", -5: "UNAVAILABLE", -6: "TIMEOUT"}
 
@@ -159,6 +160,10 @@ class PatchUpdate:
     dissipation: str = "var0"
     output: str = "haloed"
     kernel: str = "auto"     # 'auto' | 'cell': 3-D shapes have a plane-marching kernel (auto) and a thread-per-cell one
+    # 'reference': the reference's arithmetic, bit for bit (no contraction, IEEE division / sqrt).  'fast': permission to
+    # contract multiply-adds and use a branch-free reciprocal / sqrt -- within 1e-12 relative, not bitwise; committed for
+    # the headline shapes, other shapes keep the reference arithmetic (EXAHYPE_FLAG_FAST_ARITHMETIC)
+    arithmetic: str = "reference"
 
     def __post_init__(self):
         from .KernelBuilder import viable
@@ -167,8 +172,9 @@ class PatchUpdate:
         if self.model not in MODEL or self.dtype not in DTYPE:
             raise ValueError(f"unknown model/dtype {self.model}/{self.dtype}")
         if self.dissipation not in ("var0", "all") or self.output not in ("haloed", "unhaloed") \
-                or self.kernel not in ("auto", "cell"):
-            raise ValueError("dissipation must be 'var0'|'all', output 'haloed'|'unhaloed', kernel 'auto'|'cell'")
+                or self.kernel not in ("auto", "cell") or self.arithmetic not in ("reference", "fast"):
+            raise ValueError("dissipation must be 'var0'|'all', output 'haloed'|'unhaloed', kernel 'auto'|'cell', "
+                             "arithmetic 'reference'|'fast'")
         self._lib = load()
 
     @classmethod
@@ -210,7 +216,8 @@ class PatchUpdate:
         return ((FLAG_DISSIPATION_ALL if self.dissipation == "all" else 0) |
                 (FLAG_OUTPUT_UNHALOED if self.output == "unhaloed" else 0) |
                 (FLAG_LAMBDA_ACCUMULATE if accumulate_lambda else 0) |
-                (FLAG_KERNEL_CELL if self.kernel == "cell" else 0))
+                (FLAG_KERNEL_CELL if self.kernel == "cell" else 0) |
+                (FLAG_FAST_ARITHMETIC if self.arithmetic == "fast" else 0))
 
     def config(self, accumulate_lambda: bool = False) -> FvConfig:
         return FvConfig(MODEL[self.model], DTYPE[self.dtype], self.dim, self.patch_size, self.halo_size,

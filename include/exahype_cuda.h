@@ -57,7 +57,13 @@ enum {
   EXAHYPE_FLAG_LAMBDA_ACCUMULATE = 1u << 2,
   /* 3-D shapes have two kernels with identical results: plane marching (default) and thread-per-cell (this flag).
    * Ignored where only one kernel exists. */
-  EXAHYPE_FLAG_KERNEL_CELL = 1u << 3
+  EXAHYPE_FLAG_KERNEL_CELL = 1u << 3,
+  /* Permission to leave the reference's bit pattern: fused multiply-adds and a branch-free reciprocal / square root
+   * (valid for normal-range densities / heights).  Results stay within 1e-12 relative of the reference arithmetic -- the
+   * bound BASELINE.json states -- but are no longer bitwise equal to it.  Committed for the headline shapes (8^3 Euler
+   * fp64, 16^2 Euler fp64, 32^2 shallow water fp64 / fp32); other shapes keep the reference arithmetic.  The kernels
+   * execute ~14 % fewer instructions, which is what bounds them once the board runs power-limited. */
+  EXAHYPE_FLAG_FAST_ARITHMETIC = 1u << 4
 };
 
 typedef struct {

@@ -198,3 +198,29 @@ def reference_flux(q: np.ndarray, normal: int, n_out: int = 5) -> np.ndarray:
 def reference_max_eigenvalue(q: np.ndarray, normal: int) -> float:
     q = np.ascontiguousarray(q, dtype=np.float64)
     return float(_ref().ref_max_eigenvalue(q.ctypes.data, int(normal)))
+
+
+def reference_compiled_rate(min_seconds: float = 2.0):
+    """Interior cell-updates/s of the reference's own committed kernel (``Unit test/test.cpp`` + ``Functions.cpp``,
+    compiled from where they lie: ``oracle/_ref/libexahype_ref_fast.so``, ``-O3 -march=native``) on its hard-wired shape --
+    one 4x4 2-D patch with 5 + 5 variables, one thread, as the reference runs.  Returns ``(rate, description)`` or
+    ``None`` when the prebuilt library is not there."""
+    import time
+    path = os.path.join(_HERE, "_ref", "libexahype_ref_fast.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.ref_time_step_repeat.restype = None
+    lib.ref_time_step_repeat.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_long]
+    q0 = fill_sin(REFERENCE_CONFIG, 1).ravel().copy()
+    q = q0.copy()
+    reps, calls, elapsed = 20000, 0, 0.0
+    lib.ref_time_step_repeat(q0.ctypes.data, q.ctypes.data, 1.0, 1000)
+    while elapsed < min_seconds:
+        t0 = time.perf_counter()
+        lib.ref_time_step_repeat(q0.ctypes.data, q.ctypes.data, 1.0, reps)
+        elapsed += time.perf_counter() - t0
+        calls += reps
+    return 16 * calls / elapsed, (f"reference's committed kernel (Unit test/test.cpp + Functions.cpp, g++ -O3 -march=native), "
+                                  f"its hard-wired 4x4 2-D patch with 5+5 variables, {calls} calls in {elapsed:.1f} s, 1 thread, "
+                                  f"incl. its five new[]/delete[] per call")

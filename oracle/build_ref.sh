@@ -15,4 +15,9 @@ mkdir -p "$here/_ref"
 "${OCXX:-$( [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++ )}" -std=c++17 -O2 -ffp-contract=off -fPIC -shared -Wl,-Bsymbolic \
     -I"$ref" "$here/ref_shim.cpp" "$ref/test.cpp" "$ref/Functions.cpp" \
     -o "$here/_ref/libexahype_ref.so"
-echo "built $here/_ref/libexahype_ref.so"
+# the same sources as a caller who wants speed would build them (-O3 -march=native, contraction left to the compiler):
+# only ever TIMED (bench.py cpu_baseline.reference_compiled), never compared bit for bit
+"${OCXX:-$( [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++ )}" -std=c++17 -O3 -march=native -fPIC -shared -Wl,-Bsymbolic \
+    -I"$ref" "$here/ref_shim.cpp" "$ref/test.cpp" "$ref/Functions.cpp" \
+    -o "$here/_ref/libexahype_ref_fast.so"
+echo "built $here/_ref/libexahype_ref.so and libexahype_ref_fast.so"

@@ -34,4 +34,12 @@ void ref_flux(const double* Q, int normal, double* F) { Flux(Q, normal, F); }
 double ref_max_eigenvalue(const double* Q, int normal) { return maxEigenvalue(Q, normal); }
 double ref_max(double* a, double* b) { return max(a, b); }
 int ref_n_values(void) { return 360; }
+// `reps` calls of the committed kernel on a fresh copy of Q0 each (360 doubles; the copy is part of what a caller of
+// time_step(Q, dt) does per patch anyway): what bench.py times as cpu_baseline.reference_compiled
+void ref_time_step_repeat(const double* Q0, double* Q, double dt, long reps) {
+  for (long r = 0; r < reps; ++r) {
+    for (int i = 0; i < 360; ++i) Q[i] = Q0[i];
+    time_step(Q, dt);
+  }
+}
 }
