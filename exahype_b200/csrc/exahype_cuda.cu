@@ -98,7 +98,8 @@ int validate(const exahype_fv_config* cfg) {
   if (cfg->halo < 1) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "the Rusanov update reads one halo layer: halo_size must be >= 1");
   if (cfg->n_real < 1 || cfg->n_aux < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_real must be >= 1 and n_aux >= 0");
   if (cfg->dtype != EXAHYPE_DTYPE_F64 && cfg->dtype != EXAHYPE_DTYPE_F32) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
-  if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
+  if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE && cfg->model != EXAHYPE_MODEL_SWE_SOURCE)
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
   if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE |
                      EXAHYPE_FLAG_KERNEL_CELL | EXAHYPE_FLAG_FAST_ARITHMETIC))
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown flag bits 0x%x", cfg->flags);
@@ -181,7 +182,7 @@ int exahype_cuda_fill_synthetic(const exahype_fv_config* cfg, void* q, int64_t f
   if (n_cells == 0) return EXAHYPE_OK;
   if (!q) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q must not be null");
   const int nv = cfg->n_real + cfg->n_aux;
-  if ((cfg->model == EXAHYPE_MODEL_EULER && cfg->n_real < cfg->dim + 2) || (cfg->model == EXAHYPE_MODEL_SWE && nv < 3))
+  if ((cfg->model == EXAHYPE_MODEL_EULER && cfg->n_real < cfg->dim + 2) || (cfg->model != EXAHYPE_MODEL_EULER && nv < 3))
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "too few variables for the model's synthetic state");
   cudaError_t err = exahype::fill_synthetic(cfg, q, first_cell, n_cells, seed, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "fill_synthetic_kernel launch");

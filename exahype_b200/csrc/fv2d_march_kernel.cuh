@@ -228,6 +228,7 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
         qc[v] = Upd::dissipation(qc[v], q[MID][v], xr[(NR + 1 + v) * XS], xl[(NR + 1 + v) * XS], l1_mid, l_plus, l_minus,
                                  m.dt);
     }
+    fv_apply_source<Phys, Upd, T>(qc, q[MID], m.dt);          // "Q_copy = Q_copy + dt*S" (families with a source term)
     if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
   }
 

@@ -271,6 +271,7 @@ __device__ __forceinline__ void march_interior_step(MarchStream<C>& ms, const Fv
         qc[v] = Upd::dissipation(qc[v], q[MID][v], qm[(cell + 1) * NV + v], qm[(cell - 1) * NV + v], lk[MID], l_plus,
                                  l_minus, dt);
     }
+    fv_apply_source<Phys, Upd, T>(qc, q[MID], dt);            // "Q_copy = Q_copy + dt*S" (families with a source term)
     T* dst = ms.stage + wb * (C::STAGE_SEGS * C::SEG_PITCH) + st;
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = qc[v];

@@ -403,6 +403,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
         qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], EARLY ? qn_k[c][1] : qm[(cell + 1) * NV + v],
                                  EARLY ? qn_k[c][0] : qm[(cell - 1) * NV + v], lk[c], l_plus, l_minus, dt);
     }
+    fv_apply_source<Phys, Upd, T>(qc, w.q[MID][c], dt);       // "Q_copy = Q_copy + dt*S" (families with a source term)
     T* dst = ps.stage + wb * C::STAGE_ELEMS + ln.st + c * (C::P * NV);
 #pragma unroll
     for (int v = 0; v < NV; ++v) dst[v] = qc[v];

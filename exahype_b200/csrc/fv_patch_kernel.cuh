@@ -521,6 +521,7 @@ fv_step_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patc
             qc[v] = Upd::dissipation(qc[v], q[r][v], q_plus, q_minus, lam[r][n], l_plus, l_minus, dt_cell);
           }
         }
+        fv_apply_source<Phys, Upd, T>(qc, q[r], dt_cell);     // "Q_copy = Q_copy + dt*S" (families with a source term)
         T* dst = stage + e * NV;
 #pragma unroll
         for (int v = 0; v < NV; ++v) dst[v] = qc[v];

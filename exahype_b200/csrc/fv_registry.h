@@ -112,4 +112,10 @@ inline FvEntry march_entry(int model, int dtype, int dim, int P, int H, int nr, 
   return make_entry<March::template Dense, March::template Gather, Cell::template Dense>(model, dtype, dim, P, H, nr, na);
 }
 
+// marching kernel only (no thread-per-cell alternative: the shape's tile does not fit shared memory, or none is wanted)
+template <class March>
+inline FvEntry march_only_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
+  return make_entry<March::template Dense, March::template Gather, NoKernel>(model, dtype, dim, P, H, nr, na);
+}
+
 }  // namespace exahype

@@ -25,17 +25,12 @@ constexpr int EU = EXAHYPE_MODEL_EULER, SWE = EXAHYPE_MODEL_SWE, F64 = EXAHYPE_D
 #define EXAHYPE_FAST_3D_SB 2     // output staging buffers per warp
 #endif
 
-template <class March>
-inline FvEntry fast_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
-  return make_entry<March::template Dense, March::template Gather, NoKernel>(model, dtype, dim, P, H, nr, na);
-}
-
 const std::vector<FvEntry>& entries() {
   static const std::vector<FvEntry> v = {
-      fast_entry<Pair3dFamily<E3, double, 8, 1, 8, EXAHYPE_FAST_3D_PR, EXAHYPE_FAST_3D_SB>>(EU, F64, 3, 8, 1, 5, 0),   // C3 / C5
-      fast_entry<March2dFamily<E2, double, 16, 1, 4, 4, 2>>(EU, F64, 2, 16, 1, 4, 0),                                 // C2
-      fast_entry<March2dFamily<SW, double, 32, 1, 4, 4, 3>>(SWE, F64, 2, 32, 1, 3, 1),                                // C4
-      fast_entry<March2dFamily<SW, float, 32, 1, 4, 6, 4>>(SWE, F32, 2, 32, 1, 3, 1),                                 // C4 fp32 (contraction only)
+      march_only_entry<Pair3dFamily<E3, double, 8, 1, 8, EXAHYPE_FAST_3D_PR, EXAHYPE_FAST_3D_SB>>(EU, F64, 3, 8, 1, 5, 0),   // C3 / C5
+      march_only_entry<March2dFamily<E2, double, 16, 1, 4, 4, 2>>(EU, F64, 2, 16, 1, 4, 0),                                 // C2
+      march_only_entry<March2dFamily<SW, double, 32, 1, 4, 4, 3>>(SWE, F64, 2, 32, 1, 3, 1),                                // C4
+      march_only_entry<March2dFamily<SW, float, 32, 1, 4, 6, 4>>(SWE, F32, 2, 32, 1, 3, 1),                                 // C4 fp32 (contraction only)
   };
   return v;
 }

@@ -8,7 +8,8 @@
 namespace exahype {
 namespace {
 using SW = SwePhysics<3, 1>;
-constexpr int SWE = EXAHYPE_MODEL_SWE, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_DTYPE_F32;
+using SWS = SweSourcePhysics<3, 3>;      // + bathymetry source term, aux = (b, db/dx, db/dy)   
+constexpr int SWE = EXAHYPE_MODEL_SWE, SWES = EXAHYPE_MODEL_SWE_SOURCE, F64 = EXAHYPE_DTYPE_F64, F32 = EXAHYPE_DTYPE_F32;
 
 #ifndef EXAHYPE_SWE32F_MINB
 #define EXAHYPE_SWE32F_MINB 6   // CTAs (of four warps) per SM of the fp32 32x32 row-marching kernel: 24 warps at <= 85 registers
@@ -24,6 +25,11 @@ const std::vector<FvEntry>& entries() {
       march_entry<March2dFamily<SW, float, 32, 1, 4, EXAHYPE_SWE32F_MINB, EXAHYPE_SWE32F_PF>, CellFamily<SW, float, 2, 32, 1, 1, 512, 1>>(SWE, F32, 2, 32, 1, 3, 1),
       march_entry<March2dFamily<SW, double, 16, 1, 4, 4, 2>, CellFamily<SW, double, 2, 16, 1, 1, 256, 2>>(SWE, F64, 2, 16, 1, 3, 1),
       march_entry<March2dFamily<SW, float, 16, 1, 4, 4, 3>, CellFamily<SW, float, 2, 16, 1, 1, 256, 2>>(SWE, F32, 2, 16, 1, 3, 1),
+      // with the source statement: 48-byte cells (6 fp64 values) go through 128-bit accesses
+      march_only_entry<March2dFamily<SWS, double, 32, 1, 4, 3, 2>>(SWES, F64, 2, 32, 1, 3, 3),     // (a thread-per-cell tile would not fit)
+      march_entry<March2dFamily<SWS, float, 32, 1, 4, 4, 3>, CellFamily<SWS, float, 2, 32, 1, 1, 512, 1>>(SWES, F32, 2, 32, 1, 3, 3),
+      march_entry<March2dFamily<SWS, double, 16, 1, 4, 3, 2>, CellFamily<SWS, double, 2, 16, 1, 1, 256, 2>>(SWES, F64, 2, 16, 1, 3, 3),
+      cell_entry<CellFamily<SWS, double, 2, 4, 1, 16, 256, 2>>(SWES, F64, 2, 4, 1, 3, 3),
   };
   return v;
 }

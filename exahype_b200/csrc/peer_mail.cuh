@@ -1,11 +1,16 @@
 // Mailbox protocol of the one-shot all-reduce(max) over NVLink peer memory (peer_reduce.cu), shared by the standalone
 // reducer kernels and by patch kernels that run the exchange themselves (fv3d_pair_kernel.cuh).
 //
-// Every rank owns a mailbox [2][world] of (value bits, sequence number), mapped into every peer through CUDA IPC.  For
-// exchange number `seq`, rank r stores (value, seq) into slot [seq & 1][r] of every peer's mailbox (its own included);
-// a consumer reads its own slots [seq & 1][t] once their sequence number is seq.  Two slots by sequence parity are
-// enough: a rank publishes exchange s+1 only after it has consumed exchange s, and it can consume s only after every
-// peer has published s -- which a peer does after it has consumed s-1, the previous tenant of the other slot.
+// Every rank owns a mailbox [2][world] of 64-bit words, mapped into every peer through CUDA IPC.  A word carries the value
+// (double or float bits; the reduced quantity is a maximum of absolute eigenvalues, so its sign bit is free) and, in bit
+// 63, the epoch of the exchange it belongs to.  For exchange number `seq`, rank r stores its word into slot [seq & 1][r] of
+// every peer's mailbox (its own included) with ONE relaxed 8-byte store -- value and flag cannot tear, no fence is needed
+// on either side -- and a consumer polls its own slots [seq & 1][t] until their epoch bit is that of `seq`:
+// (seq >> 1) & 1, which flips every time a slot is reused.  Two slots by sequence parity and one epoch bit are enough:
+// a rank publishes exchange s+1 only after it has consumed exchange s, and it can consume s only after every peer has
+// published s -- which a peer does after it has consumed s-1; so when a consumer looks for s, the slot holds either s
+// or s-2 (the opposite epoch), never anything older.  Mailboxes start out as "exchange -1 / 0": slot 0 all zero bits,
+// slot 1 with the epoch bit set (peer_reducer_create).
 //
 // Two ways to run one exchange:
 //   blocking     publish, then wait for all peers, in the same place (stand-alone kernel; the last warp of a patch
@@ -23,9 +28,10 @@
 namespace exahype {
 
 struct PeerMail {
-  unsigned long long bits;   // the value (double or float bits)
-  unsigned long long seq;    // exchange number the value belongs to (0 = never written)
+  unsigned long long word;   // bit 63: epoch of the exchange, bits 62..0: the value's bits (sign bit cleared)
 };
+constexpr unsigned long long kMailEpochBit = 1ull << 63;
+__host__ __device__ inline unsigned long long mail_epoch(unsigned long long seq) { return ((seq >> 1) & 1ull) << 63; }
 
 // who does what inside a patch kernel: nothing | epilogue publishes and waits | prologue consumes + epilogue publishes |
 // prologue consumes only (the kernel has no exchange epilogue: a one-warp kernel behind it publishes)
@@ -66,12 +72,9 @@ struct FvPeerFuse {
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -101,13 +104,12 @@ template <> struct MailBits<float> {
   static __device__ __forceinline__ float poison() { return __uint_as_float(0x7fc00000u); }
 };
 
-// publish v as this rank's value of exchange `seq` in peer t's mailbox
+// publish v as this rank's value of exchange `seq` in peer t's mailbox: one relaxed 8-byte store over NVLink
 template <typename T>
 __device__ __forceinline__ void peer_publish_to(PeerMail* const* peers, int world, int rank, int t, unsigned long long seq,
                                                 T v) {
   PeerMail* dst = peers[t] + (int)(seq & 1ull) * world + rank;
-  st_relaxed_sys(&dst->bits, MailBits<T>::to(v));
-  st_release_sys(&dst->seq, seq);                     // the value is visible before its sequence number
+  st_relaxed_sys(&dst->word, (MailBits<T>::to(v) & ~kMailEpochBit) | mail_epoch(seq));
 }
 // wait for peer t's value of exchange `seq` in this rank's mailbox; a timeout raises the sticky error flag and returns
 // NaN, so that everything derived from the exchange is visibly poisoned instead of silently rank-local
@@ -115,14 +117,16 @@ template <typename T>
 __device__ __forceinline__ T peer_wait_for(const PeerMail* mine, int world, int t, unsigned long long seq,
                                            long long timeout_cycles, int* error) {
   const PeerMail* src = mine + (int)(seq & 1ull) * world + t;
+  const unsigned long long epoch = mail_epoch(seq);
   const long long t0 = clock64();
-  while (ld_acquire_sys(&src->seq) != seq) {
+  unsigned long long w;
+  while (((w = ld_relaxed_sys(&src->word)) & kMailEpochBit) != epoch) {
     if (clock64() - t0 > timeout_cycles) {
       peer_raise_timeout(error);
       return MailBits<T>::poison();
     }
   }
-  return MailBits<T>::from(ld_acquire_sys(&src->bits));
+  return MailBits<T>::from(w & ~kMailEpochBit);
 }
 // One thread's share of a blocking exchange: publish v to peer t, wait for peer t's value.
 template <typename T>
@@ -154,12 +158,14 @@ __device__ __forceinline__ T peer_wait_max(const PeerMail* mine, int world, int 
   for (int base = 0; base < world && !timed_out; base += 32) {
     const int t = (base + lane < world) ? base + lane : world - 1;
     const PeerMail* src = mine + (int)(seq & 1ull) * world + t;
+    const unsigned long long epoch = mail_epoch(seq);
     const long long t0 = clock64();
-    while (!__all_sync(0xffffffffu, ld_acquire_sys(&src->seq) == seq)) {
+    unsigned long long w;
+    while (!__all_sync(0xffffffffu, ((w = ld_relaxed_sys(&src->word)) & kMailEpochBit) == epoch)) {
       if (__any_sync(0xffffffffu, clock64() - t0 > timeout_cycles)) { timed_out = true; break; }
     }
     if (!timed_out) {
-      const T got = MailBits<T>::from(ld_acquire_sys(&src->bits));
+      const T got = MailBits<T>::from(w & ~kMailEpochBit);
       best = (best < got) ? got : best;
     }
   }

@@ -3,7 +3,7 @@
 //
 // The reference has no distributed code; the exchange this path needs is ONE scalar per step, so
 // the collective is pure latency.  ncclAllReduce of 8 bytes costs ~17 us per step on 2 GPUs; here every rank owns a
-// mailbox [2][world] in device memory, opened by every peer through CUDA IPC (protocol: peer_mail.cuh).
+// mailbox [2][world] of 8-byte words in device memory, opened by every peer through CUDA IPC (protocol: peer_mail.cuh).
 //
 //   PeerReducer  the mailboxes + the blocking exchange as one tiny stream-ordered kernel
 //                (peer_allreduce_max_kernel: thread t publishes to peer t and waits for peer t);
@@ -132,7 +132,11 @@ cudaError_t peer_reducer_create(PeerReducer** out, int world, int rank) {
   r->peers.assign(world, nullptr);
   cudaError_t err = cudaGetDevice(&r->device);
   if (err == cudaSuccess) err = cudaMalloc(&r->mine, sizeof(PeerMail) * 2 * world);
-  if (err == cudaSuccess) err = cudaMemset(r->mine, 0, sizeof(PeerMail) * 2 * world);
+  if (err == cudaSuccess) {   // "exchange 0 / -1": slot 0 zero, slot 1 with the epoch bit set (peer_mail.cuh)
+    std::vector<PeerMail> init(2 * (size_t)world, PeerMail{0ull});
+    for (int t = 0; t < world; ++t) init[(size_t)world + t].word = kMailEpochBit;
+    err = cudaMemcpy(r->mine, init.data(), sizeof(PeerMail) * 2 * world, cudaMemcpyHostToDevice);
+  }
   if (err == cudaSuccess) err = cudaMalloc(&r->d_peers, sizeof(PeerMail*) * world);
   if (err == cudaSuccess) err = cudaHostAlloc(&r->h_error, sizeof(int), cudaHostAllocMapped);
   if (err == cudaSuccess) {

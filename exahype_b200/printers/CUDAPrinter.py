@@ -68,6 +68,11 @@ class RusanovProgram:
     # cell context: 'x' volume centre, 'h' volume size, 'X' patch centre, 'H' patch size, 't', 'dt'
     flux_args: List[str] = field(default_factory=lambda: ["Q", "normal", "F"])
     eigen_args: List[str] = field(default_factory=lambda: ["Q", "normal"])
+    # optional source term: `sourceTerm(Q[0], S[0])` on the ORIGINAL state followed by
+    # `Q_copy[0] = Q_copy[0] + dt*S[0]`, after the dissipation statements
+    source_fn: Optional[str] = None
+    source_tmp: Optional[str] = None
+    source_update: Optional[str] = None       # device expression in (qc, s, dt)
 
     @property
     def context(self) -> bool:
@@ -154,6 +159,7 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
         raise UnsupportedKernel("last statement must copy the working item back into the input")
 
     flux_calls, eig_calls, flux_upd, diss_upd = {}, {}, {}, {}
+    source_call: Dict[str, object] = {}
     normal_name, normals = None, {}
     pending_normal = None
     # scalar members of the CellData object (kernel-generator.py:15-19: dt, t, cellCentre, cellSize with parent=Data)
@@ -195,7 +201,7 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
             roles.append("copy-out"); continue
         if struct == -1 and isinstance(lhs, Symbol) and str(lhs) in k.directional_consts:
             normal_name = str(lhs); pending_normal = int(rhs); roles.append(f"{lhs} = {rhs}"); continue
-        if fn_name(lhs) and rhs is None:                                   # Flux(Qc[c], normal, F_d[c])
+        if fn_name(lhs) and rhs is None and direction >= 1:                # Flux(Qc[c], normal, F_d[c])
             args = lhs.args
             if len(args) < 3 or base_of(args[0]) != q_work or not isinstance(args[-1], Indexed):
                 raise UnsupportedKernel(f"flux call {lhs} must be f({q_work}[c], {normal_name}, tmp[c])")
@@ -214,6 +220,18 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
                 flux_upd[direction] = (lhs, rhs, struct); roles.append(f"flux update axis {direction}"); continue
             if q_in in used:
                 diss_upd[direction] = (lhs, rhs, struct); roles.append(f"dissipation axis {direction}"); continue
+        if fn_name(lhs) and rhs is None and direction < 0:                  # sourceTerm(Q[c], S[c])
+            args = lhs.args
+            if len(args) != 2 or base_of(args[0]) != q_in or not isinstance(args[1], Indexed) or base_of(args[1]) in (q_in, q_work):
+                raise UnsupportedKernel(f"source call {lhs} must be f({q_in}[c], tmp[c]): the source is evaluated on the original state")
+            if source_call:
+                raise UnsupportedKernel("more than one source call")
+            source_call.update(fn=fn_name(lhs), tmp=base_of(args[1]))
+            roles.append("source call"); continue
+        if isinstance(lhs, Indexed) and base_of(lhs) == q_work and isinstance(rhs, sympy.Expr) and source_call \
+                and source_call["tmp"] in {base_of(a) for a in rhs.atoms(Indexed)} and direction < 0:
+            source_call["update"] = (lhs, rhs, struct)
+            roles.append("source update"); continue
         raise UnsupportedKernel(f"statement {pos} ({lhs} = {rhs}) is not part of the Rusanov patch update")
 
     axes = list(range(1, dim + 1))
@@ -299,11 +317,36 @@ def analyse(kernel: KernelBuilder) -> RusanovProgram:
     widths = [w for name, w in k.item_struct.items() if name in str([lhs, rhs])] + [struct]
     dissipation_all = min(widths) >= 1
 
+    source_text = None
+    if source_call:
+        if "update" not in source_call:
+            raise UnsupportedKernel("a source call needs the statement that adds dt*S to the working item")
+        if roles.index("source call") < max(i for i, r in enumerate(roles) if r.startswith("dissipation")):
+            raise UnsupportedKernel("the source statements follow the dissipation statements")
+        lhs, rhs, struct = source_call["update"]
+        names = {}
+        for a in rhs.atoms(Indexed):
+            if any(sympy.simplify(idx - k.all_items[str(k.indexes[level])]) != 0
+                   for level, idx in enumerate(a.indices[: 1 + dim])):
+                raise UnsupportedKernel(f"{a}: the source update reads the centre cell only")
+            names[a] = {q_work: "qc", source_call["tmp"]: "s"}.get(base_of(a))
+            if names[a] is None:
+                raise UnsupportedKernel(f"unexpected access {a} in the source update")
+        for sym in rhs.free_symbols - set().union(*[a.free_symbols for a in rhs.atoms(Indexed)]):
+            if str(sym) not in dt_names:
+                raise UnsupportedKernel(f"symbol {sym} is not available inside the kernel")
+        source_text = _StatementPrinter(names, None).doprint(rhs)
+        if dt is not None and dt != "dt":
+            source_text = source_text.replace(dt, "dt")
+        if min([w for name, w in k.item_struct.items() if name in str([lhs, rhs])] + [struct]) < 1:
+            raise UnsupportedKernel("the source update must run over the unknowns (struct=True)")
+
     return RusanovProgram(q_in=q_in, q_work=q_work, flux_tmp=flux_tmp, eigen_tmp=eigen_tmp,
                           flux_fn=next(iter(flux_fn)), eigen_fn=next(iter(eigen_fn)), max_fn=max_fn,
                           normal=normal_name or "normal", normals=[normals[d] for d in axes], dt=dt,
                           flux_update=flux_text, dissipation=diss_text, dissipation_all=dissipation_all, roles=roles,
-                          flux_args=flux_arg_tags[1], eigen_args=eigen_arg_tags[1])
+                          flux_args=flux_arg_tags[1], eigen_args=eigen_arg_tags[1],
+                          source_fn=source_call.get("fn"), source_tmp=source_call.get("tmp"), source_update=source_text)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -425,7 +468,9 @@ class CUDAPrinter(CodePrinter):
         else:
             self.template = "cell"
         elem = 8 if dtype == "f64" else 4
-        G, nt, minb = pick_geometry(k.dim, k.patch_size, k.halo_size, k.n_real, k.n_aux, elem)
+        # tile geometry of the thread-per-cell template (the marching templates pick theirs at compile time)
+        G, nt, minb = pick_geometry(k.dim, k.patch_size, k.halo_size, k.n_real, k.n_aux, elem) if self.template == "cell" \
+            else (1, 256, 1)
         self.patches_per_tile = patches_per_tile or G
         self.threads = threads or nt
         self.min_ctas = minb
@@ -482,10 +527,13 @@ class CUDAPrinter(CodePrinter):
             fam = fb.builtin
             if fam == "euler":
                 return f"using Physics = ::exahype::EulerPhysics<{dim}, {nr}, {na}>;   // csrc/physics.cuh\n"
-            if fam == "swe":
+            if fam in ("swe", "swe_source"):
                 if dim != 2:
                     raise UnsupportedKernel("the shallow-water family is 2-D")
-                return f"using Physics = ::exahype::SwePhysics<{nr}, {na}>;   // csrc/physics.cuh\n"
+                if (fam == "swe_source") != bool(p.source_fn):
+                    raise UnsupportedKernel("model 'swe_source' goes with a declaration that has the source statements, 'swe' with one that has none")
+                cls = "SweSourcePhysics" if fam == "swe_source" else "SwePhysics"
+                return f"using Physics = ::exahype::{cls}<{nr}, {na}>;   // csrc/physics.cuh\n"
             raise UnsupportedKernel(f"unknown builtin physics '{fam}'")
 
         ctx = self.context
@@ -531,9 +579,18 @@ class CUDAPrinter(CodePrinter):
             out.append("    return T(0);\n")
         else:
             out.append(f"    return {scope(eb)}{p.eigen_fn}({self._call_args(p.eigen_args)});\n")
-        out.append("  }\n};\n")
+        out.append("  }\n")
+        if p.source_fn:           # void sourceTerm(const T* Q, T* S) in the style of Functions.h
+            sb = self._body_of(p.source_fn)
+            if sb is not None and (sb.expressions or sb.builtin):
+                raise UnsupportedKernel("a generated source term needs a device-source body (or model='swe_source')")
+            out.append("  static constexpr bool HAS_SOURCE = true;\n"
+                       "  template <typename T>\n"
+                       "  static __device__ __forceinline__ void source(const T (&q)[NV], T (&S)[NR]) {\n"
+                       f"    {scope(sb)}{p.source_fn}(q, S);\n  }}\n")
+        out.append("};\n")
         pre = ""
-        for b in (fb, eb):
+        for b in (fb, eb, self._body_of(p.source_fn) if p.source_fn else None):
             if b is not None and b.source and b.source not in pre:
                 pre += b.source.rstrip() + "\n\n"
         # the user's functions live in their own namespace: a declared name such as `flux` must not collide with the
@@ -590,7 +647,11 @@ class CUDAPrinter(CodePrinter):
             f"    return {p.flux_update};\n  }}\n"
             "  template <typename T>\n"
             "  static __device__ __forceinline__ T dissipation(T qc, T q0, T q_plus, T q_minus, T l0, T l_plus, T l_minus, T dt) {\n"
-            f"    return {p.dissipation};\n  }}\n}};\n\n}}  // namespace\n\n")
+            f"    return {p.dissipation};\n  }}\n"
+            + ("  template <typename T>\n"
+               "  static __device__ __forceinline__ T source(T qc, T s, T dt) {\n"
+               f"    return {p.source_update};\n  }}\n" if p.source_update else "")
+            + "};\n\n}  // namespace\n\n")
         parts.append(
             f"// Drop-in for the reference's generated `void {fname}(double* Q, double dt)` over a device-resident batch.\n"
             "// flags: bit 1 = un-haloed output, bit 2 = accumulate into *lambda_max (include/exahype_cuda.h).\n"

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # EXAHYPE_CUDA_LIB points the binding at another build of the same ABI (kernel-tuning experiments)
 LIB_PATH = os.environ.get("EXAHYPE_CUDA_LIB") or os.path.join(_HERE, "libexahype_cuda.so")
 
-MODEL = {"euler": 0, "swe": 1}
+MODEL = {"euler": 0, "swe": 1, "swe_source": 2}   # swe_source: + bathymetry source term, aux = (b, db/dx, db/dy)
 DTYPE = {"f64": 0, "f32": 1}
 FLAG_DISSIPATION_ALL = 1 << 0
 FLAG_OUTPUT_UNHALOED = 1 << 1

@@ -41,7 +41,11 @@ enum {
 };
 
 /* physics families with committed hand-written functors (csrc/physics.cuh) */
-enum { EXAHYPE_MODEL_EULER = 0, EXAHYPE_MODEL_SWE = 1 };
+/* EXAHYPE_MODEL_SWE_SOURCE: shallow water with the bathymetry source term: cell variables
+ * (h, hu, hv | b, db/dx, db/dy), n_real = 3, n_aux = 3; one more statement after the dissipation,
+ * Q_copy = Q_copy + dt*S with S = (0, -g h db/dx, -g h db/dy) of the original state.  The reference has only the solver
+ * signature sourceTerm(Q, x, h, t, dt, S) ("Unit test/correctness_test.cpp":16-23); the definition is this repository's. */
+enum { EXAHYPE_MODEL_EULER = 0, EXAHYPE_MODEL_SWE = 1, EXAHYPE_MODEL_SWE_SOURCE = 2 };
 enum { EXAHYPE_DTYPE_F64 = 0, EXAHYPE_DTYPE_F32 = 1 };
 
 /* flags */

@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-MODEL_EULER, MODEL_SWE = 0, 1
+MODEL_EULER, MODEL_SWE, MODEL_SWE_SOURCE = 0, 1, 2
 RANGES_HEAD, RANGES_COMMITTED = 0, 1
 DISS_VAR0, DISS_ALL = 0, 1
 

@@ -31,8 +31,9 @@ static int fvo_make_geom(const fvo_config* c, fvo_geom* g) {
   if (c->halo < 1) return -4;                          /* the +-1 stencil needs one halo layer */
   if (c->n_real < 1 || c->n_real > FVO_MAX_NR || c->n_aux < 0) return -5;
   if (c->model == FVO_MODEL_EULER && c->n_real < c->dim + 2) return -6;
-  if (c->model == FVO_MODEL_SWE && (c->dim != 2 || c->n_real < 3)) return -6;
-  if (c->model != FVO_MODEL_EULER && c->model != FVO_MODEL_SWE) return -7;
+  if ((c->model == FVO_MODEL_SWE || c->model == FVO_MODEL_SWE_SOURCE) && (c->dim != 2 || c->n_real < 3)) return -6;
+  if (c->model == FVO_MODEL_SWE_SOURCE && c->n_aux < 3) return -6;     /* b, db/dx, db/dy */
+  if (c->model != FVO_MODEL_EULER && c->model != FVO_MODEL_SWE && c->model != FVO_MODEL_SWE_SOURCE) return -7;
   g->dim = c->dim; g->P = c->patch_size; g->h = c->halo; g->S = g->P + 2 * g->h;
   g->nr = c->n_real; g->na = c->n_aux; g->nv = g->nr + g->na;
   g->ncell = 1;
@@ -194,6 +195,15 @@ static int fvo_make_cells(const fvo_geom* g, int ranges, fvo_cells* c) {
     return (a < b) ? b : a;                                                                     \
   }                                                                                             \
                                                                                                 \
+  /* bathymetry source in the style of sourceTerm(Q, x, h, t, dt, S), correctness_test.cpp:16-23: aux = (b, bx, by) */ \
+  static void swe_source_##SFX(const T* Q, int nr, T* S) {                                      \
+    const T G = (T)9.81;                                                                        \
+    const T gh = G * Q[0];                                                                      \
+    for (int v = 0; v < nr; ++v) S[v] = (T)0;                                                   \
+    S[1] = -gh * Q[nr + 1];                                                                     \
+    S[2] = -gh * Q[nr + 2];                                                                     \
+  }                                                                                             \
+                                                                                                \
   static inline T maxp_##SFX(const T* a, const T* b) { /* Functions.cpp:64-66 */               \
     return (*a < *b) ? *b : *a;                                                                 \
   }                                                                                             \
@@ -251,6 +261,14 @@ static int fvo_make_cells(const fvo_geom* g, int ranges, fvo_cells* c) {
                 Qc[(size_t)c * nv + v];                                                         \
       }                                                                                         \
     }                                                                                           \
+    /* source term (8f-3): S of the ORIGINAL state, Q_copy = Q_copy + dt*S, interior cells */    \
+    if (cfg->model == FVO_MODEL_SWE_SOURCE)                                                     \
+      for (int k = 0; k < cl->n_interior; ++k) {                                                \
+        const int c = cl->interior[k];                                                          \
+        T S[FVO_MAX_NR];                                                                        \
+        swe_source_##SFX(Q + (size_t)c * nv, nr, S);                                            \
+        for (int v = 0; v < nr; ++v) Qc[(size_t)c * nv + v] = Qc[(size_t)c * nv + v] + dt * S[v]; \
+      }                                                                                         \
     /* test.cpp:96-104 : interior copy-back, all variables; plus the patch's max eigenvalue     \
      * over interior cells of the INPUT state (not in the reference) */         \
     T lam = (T)0;                                                                               \

@@ -27,7 +27,11 @@
 extern "C" {
 #endif
 
-enum { FVO_MODEL_EULER = 0, FVO_MODEL_SWE = 1 };
+/* SWE_SOURCE: shallow water with the bathymetry source term (no reference counterpart beyond the
+ * signature sourceTerm(Q, x, h, t, dt, S) of "Unit test/correctness_test.cpp":16-23): q = (h, hu, hv | b, db/dx, db/dy),
+ * S = (0, -g h db/dx, -g h db/dy) evaluated on the ORIGINAL state; after the dissipation statements, interior cells,
+ * v < n_real:  Q_copy = Q_copy + dt*S. */
+enum { FVO_MODEL_EULER = 0, FVO_MODEL_SWE = 1, FVO_MODEL_SWE_SOURCE = 2 };
 /* HEAD: flux/eigen on cells {full along n, interior across} (CPPPrinter.py:132-137).
  * COMMITTED: the transposed ranges found in Unit test/test.cpp:22-23,32-33. */
 enum { FVO_RANGES_HEAD = 0, FVO_RANGES_COMMITTED = 1 };

@@ -82,20 +82,27 @@ def test_fast_arithmetic_is_a_different_kernel_and_falls_back_where_none_exists(
 
 
 def test_fast_arithmetic_time_loop(torch, rt, oracle):
+    """The device-resident loop with the fast kernels: dt of the later steps derives from lambda_max of the fast
+    arithmetic (within the bound of the oracle's), and so does the state.  The input stays fixed (q_in -> q_out, as in
+    bench.py): evolving this random state in place is ill-conditioned, which would test the data, not the kernel."""
     from exahype_b200.dist import TimeLoop
     upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0, output="haloed", arithmetic="fast")
     cfg = cfg_of(oracle, upd)
     q0 = oracle.fill_synthetic(cfg, 200)
-    want, dt = q0.copy(), 0.01
-    for _ in range(3):
-        _, lmax = oracle.step(cfg, want, float(dt), nthreads=4)
-        dt = 0.05 / lmax
+    cfl_dx = 0.05
+    probe = q0.copy()
+    _, lmax = oracle.step(cfg, probe, 0.01, nthreads=4)
+    dt = cfl_dx / lmax                                  # what every step after the first uses
+    want = q0.copy()
+    oracle.step(cfg, want, float(dt), nthreads=4)
     q = torch.from_numpy(q0).cuda()
-    loop = TimeLoop("f64", None, 0.05, 0.01)
+    out = q.clone()
+    loop = TimeLoop("f64", None, cfl_dx, 0.01)
     for _ in range(3):
-        upd.step_loop(loop, q, q)
+        upd.step_loop(loop, q, out)
     loop.flush()
     torch.cuda.synchronize()
-    assert np.abs(q.cpu().numpy() - want).max() <= 5e-12 * np.abs(want).max()      # three steps
-    assert abs(loop.history(3, 1)[0, 0] - dt) <= 1e-12 * dt
+    h = loop.history(0, 4)
+    assert h[0, 0] == 0.01 and abs(h[2, 0] - dt) <= RTOL_F64 * dt and abs(h[3, 0] - dt) <= RTOL_F64 * dt
+    assert np.abs(out.cpu().numpy() - want).max() <= 2 * RTOL_F64 * np.abs(want).max()
     loop.close()
