@@ -35,6 +35,8 @@ WORKLOADS = {
     "c2": ("euler", 2, 16, 1, 4, 0, "f64", 65536, "2D Euler Rusanov FV, 16x16 patches + 1 halo, batch of 65,536 patches, fp64"),
     "c4": ("swe", 2, 32, 1, 3, 1, "f64", 65536, "2D shallow-water (3 unknowns + bathymetry) Rusanov FV, 32x32 patches, batch of 65,536, fp64"),
     "c4f32": ("swe", 2, 32, 1, 3, 1, "f32", 65536, "2D shallow-water Rusanov FV, 32x32 patches, batch of 65,536, fp32"),
+    # not a BASELINE config: the source-term model of SURVEY.md 8f-3 on C4's shape, for its roofline line
+    "swe_source": ("swe_source", 2, 32, 1, 3, 3, "f64", 49152, "2D shallow water with bathymetry source term (3 unknowns + b, db/dx, db/dy), 32x32 patches, batch of 49,152, fp64"),
     "c1": ("euler", 2, 3, 1, 4, 0, "f64", 1000, "2D Euler (4 unknowns) Rusanov FV, 3x3 patches + 1 halo, batch of 1,000 patches, fp64"),
 }
 METRIC = "patch_cell_updates_per_sec"
@@ -119,7 +121,7 @@ def cpu_reference_rate(workload: str, min_seconds: float, sample_patches: int):
     import oracle as O
     model, dim, P, h, nr, na, dtype, _, _ = WORKLOADS[workload]
     cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
-                         model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
+                         model={"euler": O.MODEL_EULER, "swe": O.MODEL_SWE, "swe_source": O.MODEL_SWE_SOURCE}[model])
     threads = host_threads()
     npdt = np.float64 if dtype == "f64" else np.float32
     q0 = O.fill_synthetic(cfg, sample_patches, dtype=npdt)
@@ -148,7 +150,7 @@ def run_reference_arm(args):
     import numpy as np
     import oracle as O
     cfg = O.OracleConfig(dim=dim, patch_size=P, halo=h, n_real=nr, n_aux=na,
-                         model=O.MODEL_EULER if model == "euler" else O.MODEL_SWE)
+                         model={"euler": O.MODEL_EULER, "swe": O.MODEL_SWE, "swe_source": O.MODEL_SWE_SOURCE}[model])
     threads = host_threads()
     sample = min(batch, args.cpu_sample)
     npdt = np.float64 if dtype == "f64" else np.float32
@@ -415,6 +417,29 @@ def main():
             t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        # the floor of this leg on this box: plain pinned copies of the same bytes, both directions at once, on every GPU
+        # at the same time (no kernel, no chunking) -- what the host's memory system and the PCIe links give N GPUs
+        d_probe = torch.empty_like(q_out)
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def plain_copies():
+            with torch.cuda.stream(sa):
+                q_in.copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(sb):
+                host_out.copy_(d_probe, non_blocking=True)
+        plain_copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            plain_copies()
+        torch.cuda.synchronize()
+        floor_s = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([floor_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            floor_s = float(t.item())
+        del d_probe
+        q_in = synthetic_on_device(torch, upd, shard.first, batch, tdt)      # the probe overwrote it with the same bits; regenerate anyway
         es = 8 if dtype == "f64" else 4
         e2e = {"value": cells_per_step * args.e2e_steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(host_in.numel() * es) * world,
@@ -422,7 +447,11 @@ def main():
                "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
                "api": "exahype_cuda_time_step_host (chunked H2D -> kernel -> D2H over 3 stream slots)",
                "lambda_max_matches_device": bool(float(lam_e2e) == float(lam_patch.max().item())),
-               "host_numa_node": numa_node}
+               "host_numa_node": numa_node,
+               "h2d_GBs_per_gpu": host_in.numel() * es / (e2e_s / args.e2e_steps) / 1e9,
+               "plain_copy_floor_ms": 1e3 * floor_s,
+               "floor_over_e2e": floor_s / (e2e_s / args.e2e_steps),
+               "floor": "plain pinned cudaMemcpyAsync of the same bytes, H2D and D2H concurrently, all GPUs at once (max over ranks)"}
         del host_in, host_out
         runtime.load().exahype_cuda_host_pipeline_release()
         if numa_node is not None and affinity:
@@ -601,7 +630,7 @@ def verify_time_loop(torch, dist, upd, reducer, args, q_in, q_out, lam_patch, sh
     n = q_in.shape[0]
     picks = sorted(set(list(range(min(8, n))) + list(range(n // 2, min(n, n // 2 + 8))) + list(range(max(0, n - 8), n))))
     cfg = O.OracleConfig(dim=upd.dim, patch_size=upd.patch_size, halo=upd.halo_size, n_real=upd.n_real, n_aux=upd.n_aux,
-                         model=O.MODEL_EULER if upd.model == "euler" else O.MODEL_SWE,
+                         model={"euler": O.MODEL_EULER, "swe": O.MODEL_SWE, "swe_source": O.MODEL_SWE_SOURCE}[upd.model],
                          diss=O.DISS_ALL if upd.dissipation == "all" else O.DISS_VAR0)
     idx = torch.tensor(picks, device=q_in.device)
     want = q_in[idx].cpu().numpy()

@@ -77,13 +77,22 @@ struct Fv3dPairConfig {
   static constexpr bool USE_TMA_STORE = UNHALOED && ((SEG_ELEMS * (int)sizeof(T)) % 16 == 0) &&
                                         ((SEG_PITCH * (int)sizeof(T)) % 16 == 0);
 
+  // Scratch layout of F_1 / L_1 and F_2 / L_2.  fp64 with an even record width: ONE record {F[0..NR), L} of RW values per
+  // slot, moved with 128-bit shared-memory accesses (RW/2 instead of RW instructions per record; a quarter-warp of
+  // consecutive slots at 48-byte pitch is bank-conflict free).  Otherwise component planes F[v][slot], L[slot].
+  // Same bytes either way: Rj = Fj + Lj, Rk = Fk + Lk.
+  static constexpr int RW = NR + 1;
+#ifndef EXAHYPE_3D_REC_SCRATCH
+#define EXAHYPE_3D_REC_SCRATCH 1
+#endif
+  static constexpr bool REC = EXAHYPE_3D_REC_SCRATCH && sizeof(T) == 8 && (RW % 2 == 0);
   // per-warp shared memory
   static constexpr int OFF_RING = 0;
-  static constexpr int OFF_FJ = align_up(OFF_RING + R * PLANE_BYTES, 16);
-  static constexpr int OFF_FK = align_up(OFF_FJ + NR * SJ * (int)sizeof(T), 16);
-  static constexpr int OFF_LJ = align_up(OFF_FK + NR * SK * (int)sizeof(T), 16);
-  static constexpr int OFF_LK = align_up(OFF_LJ + SJ * (int)sizeof(T), 16);
-  static constexpr int OFF_STAGE = align_up(OFF_LK + SK * (int)sizeof(T), 128);
+  static constexpr int OFF_FJ = align_up(OFF_RING + R * PLANE_BYTES, 16);                      // REC: Rj [SJ][RW]
+  static constexpr int OFF_FK = align_up(OFF_FJ + (REC ? RW : NR) * SJ * (int)sizeof(T), 16);  // REC: Rk [SK][RW]
+  static constexpr int OFF_LJ = align_up(OFF_FK + (REC ? RW : NR) * SK * (int)sizeof(T), 16);
+  static constexpr int OFF_LK = align_up(OFF_LJ + (REC ? 0 : SJ) * (int)sizeof(T), 16);
+  static constexpr int OFF_STAGE = align_up(OFF_LK + (REC ? 0 : SK) * (int)sizeof(T), 128);
   static constexpr int OFF_BAR = align_up(OFF_STAGE + SB * STAGE_ELEMS * (int)sizeof(T), 16);
   static constexpr int WARP_BYTES = align_up(OFF_BAR + R * 8, 128);
   static constexpr int SMEM_BYTES = NW * WARP_BYTES;
@@ -201,8 +210,46 @@ struct PairLane {
   int sj, sk;        // scratch slots of (ja, k): partner row at sj + PJ / sk + PK
   int st;            // staging offsets of (ja, k); the partner row is st + P*NV (same segment)
   int f_cell, f_axis, f_comp_stride;
-  T *f_F, *f_L;      // where the face column's F / L go
+  T *f_F, *f_L;      // where the face column's F / L go (REC: f_F is the slot's record, f_L unused)
 };
+
+// one slot of the F / L scratch: store, load (layout per Fv3dPairConfig::REC)
+template <class C>
+__device__ __forceinline__ void pair_scratch_put(typename C::T* F_base, typename C::T* L_base, int slot, int comp_stride,
+                                                 const typename C::T (&F)[C::NR], typename C::T L) {
+  using T = typename C::T;
+  if constexpr (C::REC) {
+    double2* rec = reinterpret_cast<double2*>(F_base + slot * C::RW);
+#pragma unroll
+    for (int i = 0; i < C::RW / 2; ++i)
+      rec[i] = make_double2(2 * i < C::NR ? F[2 * i < C::NR ? 2 * i : 0] : L, 2 * i + 1 < C::NR ? F[2 * i + 1 < C::NR ? 2 * i + 1 : 0] : L);
+  } else {
+#pragma unroll
+    for (int v = 0; v < C::NR; ++v) F_base[v * comp_stride + slot] = F[v];
+    L_base[slot] = L;
+  }
+}
+template <class C>
+__device__ __forceinline__ void pair_scratch_get(const typename C::T* F_base, const typename C::T* L_base, int slot,
+                                                 int comp_stride, typename C::T (&F)[C::NR], typename C::T& L) {
+  if constexpr (C::REC) {
+    const double2* rec = reinterpret_cast<const double2*>(F_base + slot * C::RW);
+    double tmp[C::RW];
+#pragma unroll
+    for (int i = 0; i < C::RW / 2; ++i) {
+      const double2 v = rec[i];
+      tmp[2 * i] = v.x;
+      tmp[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int v = 0; v < C::NR; ++v) F[v] = tmp[v];
+    L = tmp[C::NR];
+  } else {
+#pragma unroll
+    for (int v = 0; v < C::NR; ++v) F[v] = F_base[v * comp_stride + slot];
+    L = L_base[slot];
+  }
+}
 
 // the axis-0 window of one lane: three planes x two cells, all indices compile-time
 template <class C>
@@ -277,15 +324,9 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
     T F[NR];
     Phys::template flux<2, T>(w.q[MID][c], w.pr[MID][c], F);
     lk[c] = Phys::template eigen<2, T>(w.q[MID][c], w.pr[MID][c]);
-    T* __restrict__ FkW = ps.Fk + ln.sk + c * PK;
-#pragma unroll
-    for (int v = 0; v < NR; ++v) FkW[v * SK] = F[v];
-    ps.Lk[ln.sk + c * PK] = lk[c];
+    pair_scratch_put<C>(ps.Fk, ps.Lk, ln.sk + c * PK, SK, F, lk[c]);
     // the row above (c = 0) / below (c = 1) belongs to another lane: it reads this row's F_1 / L_1 from the scratch
-    T* __restrict__ FjW = ps.Fj + ln.sj + c * PJ;
-#pragma unroll
-    for (int v = 0; v < NR; ++v) FjW[v * SJ] = fj[c][v];
-    ps.Lj[ln.sj + c * PJ] = lj[c];
+    pair_scratch_put<C>(ps.Fj, ps.Lj, ln.sj + c * PJ, SJ, fj[c], lj[c]);
     lam_local = fv_max(lam_local, fv_max(w.li[MID][c], fv_max(lj[c], lk[c])));
   }
   // this lane's face-halo column: F_axis / L_axis of the cell one layer outside the interior (one instruction stream for
@@ -307,9 +348,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
       Phys::template flux<2, T>(q, pr, F);
       L = Phys::template eigen<2, T>(q, pr);
     }
-#pragma unroll
-    for (int v = 0; v < NR; ++v) ln.f_F[v * ln.f_comp_stride] = F[v];
-    *ln.f_L = L;
+    pair_scratch_put<C>(ln.f_F, ln.f_L, 0, ln.f_comp_stride, F, L);
   }
   // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
   // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
@@ -340,10 +379,11 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int cell = ln.cell + c * S;
-    const T* __restrict__ FjR = ps.Fj + ln.sj + c * PJ;
-    const T* __restrict__ FkR = ps.Fk + ln.sk + c * PK;
-    const T* __restrict__ LjR = ps.Lj + ln.sj + c * PJ;
-    const T* __restrict__ LkR = ps.Lk + ln.sk + c * PK;
+    // the neighbours' F / L: across axis 1 the row outside the pair (above for c = 0, below for c = 1), along axis 2 both sides
+    T Fjn[NR], Ljn, Fkp[NR], Lkp, Fkm[NR], Lkm;
+    pair_scratch_get<C>(ps.Fj, ps.Lj, ln.sj + (c == 0 ? -PJ : 2 * PJ), SJ, Fjn, Ljn);
+    pair_scratch_get<C>(ps.Fk, ps.Lk, ln.sk + c * PK + 1, SK, Fkp, Lkp);
+    pair_scratch_get<C>(ps.Fk, ps.Lk, ln.sk + c * PK - 1, SK, Fkm, Lkm);
     T qc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) qc[v] = w.q[MID][c][v];
@@ -352,9 +392,9 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], w.fi[NEW][c][v], w.fi[OLD][c][v]);
 #pragma unroll
     for (int v = 0; v < NR; ++v)
-      qc[v] = (c == 0) ? Upd::flux(qc[v], fj[1][v], FjR[v * SJ - PJ]) : Upd::flux(qc[v], FjR[v * SJ + PJ], fj[0][v]);
+      qc[v] = (c == 0) ? Upd::flux(qc[v], fj[1][v], Fjn[v]) : Upd::flux(qc[v], Fjn[v], fj[0][v]);
 #pragma unroll
-    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], FkR[v * SK + 1], FkR[v * SK - 1]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], Fkp[v], Fkm[v]);
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0, 1, 2 in order (test.cpp:78-95)
     if constexpr (SHARE_MAX) {
       // max(L, L') of a pair of cells serves both: along axis 0 it is carried from the previous step (m0), inside the
@@ -365,13 +405,13 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
         qc[v] = Upd::dissipation_m(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], m_up, w.m0[c], dt);
       w.m0[c] = m_up;
       if (c == 0) {
-        const T m_minus = fv_max(LjR[-PJ], lj[0]);
+        const T m_minus = fv_max(Ljn, lj[0]);
 #pragma unroll
         for (int v = 0; v < C::DV; ++v)
           qc[v] = Upd::dissipation_m(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], mj,
                                      m_minus, dt);
       } else {
-        const T m_plus = fv_max(LjR[PJ], lj[1]);
+        const T m_plus = fv_max(Ljn, lj[1]);
 #pragma unroll
         for (int v = 0; v < C::DV; ++v)
           qc[v] = Upd::dissipation_m(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v],
@@ -383,13 +423,13 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
         qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], w.q[NEW][c][v], w.q[OLD][c][v], w.li[MID][c], w.li[NEW][c],
                                  w.li[OLD][c], dt);
       if (c == 0) {
-        const T l_minus = LjR[-PJ];
+        const T l_minus = Ljn;
 #pragma unroll
         for (int v = 0; v < C::DV; ++v)
           qc[v] = Upd::dissipation(qc[v], w.q[MID][0][v], w.q[MID][1][v], EARLY ? qn_j[0] : qm[(cell - S) * NV + v], lj[0],
                                    lj[1], l_minus, dt);
       } else {
-        const T l_plus = LjR[PJ];
+        const T l_plus = Ljn;
 #pragma unroll
         for (int v = 0; v < C::DV; ++v)
           qc[v] = Upd::dissipation(qc[v], w.q[MID][1][v], EARLY ? qn_j[1] : qm[(cell + S) * NV + v], w.q[MID][0][v], lj[1],
@@ -397,7 +437,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
       }
     }
     {
-      const T l_plus = LkR[1], l_minus = LkR[-1];
+      const T l_plus = Lkp, l_minus = Lkm;
 #pragma unroll
       for (int v = 0; v < C::DV; ++v)
         qc[v] = Upd::dissipation(qc[v], w.q[MID][c][v], EARLY ? qn_k[c][1] : qm[(cell + 1) * NV + v],
@@ -444,7 +484,7 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   PairStream<C> ps;
   ps.q_in = q_in; ps.q_out = q_out; ps.lambda_patch = lambda_patch; ps.dt = dt;
   ps.ring = reinterpret_cast<T*>(ws + C::OFF_RING);
-  ps.Fj = reinterpret_cast<T*>(ws + C::OFF_FJ);          // [NR][SJ]
+  ps.Fj = reinterpret_cast<T*>(ws + C::OFF_FJ);          // [NR][SJ]   (REC: records [SJ][RW], Lj / Lk inside)
   ps.Fk = reinterpret_cast<T*>(ws + C::OFF_FK);          // [NR][SK]
   ps.Lj = reinterpret_cast<T*>(ws + C::OFF_LJ);          // [SJ]
   ps.Lk = reinterpret_cast<T*>(ws + C::OFF_LK);          // [SK]
@@ -493,7 +533,7 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
     ln.f_axis = f_axis;
     ln.f_cell = (f_axis == 1) ? edge * S + (f_pos + H) : (f_pos + H) * S + edge;
     const int slot_in_scratch = (f_axis == 1) ? (f_side ? P + 1 : 0) * C::PJ + f_pos : f_pos * C::PK + (f_side ? P + 1 : 0);
-    ln.f_F = (f_axis == 1 ? ps.Fj : ps.Fk) + slot_in_scratch;
+    ln.f_F = (f_axis == 1 ? ps.Fj : ps.Fk) + slot_in_scratch * (C::REC ? C::RW : 1);
     ln.f_L = (f_axis == 1 ? ps.Lj : ps.Lk) + slot_in_scratch;
     ln.f_comp_stride = (f_axis == 1) ? C::SJ : C::SK;
   }

@@ -21,7 +21,8 @@ PY
   python bench.py --workload $wl --no-cpu --no-e2e --no-others --steps 20 2>/dev/null | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read())
-s=d.get('sustained') or {}
-print('$v $wl burst kernel_ms %.4f frac %.3f | sustained ms %.4f frac %.3f clocks %s' % (d['roofline']['kernel_ms'], d['roofline']['frac'], s.get('ms_per_step',0), s.get('frac_of_burst_peak',0), (s.get('clocks') or {}).get('sm_mhz')))"
+s=d.get('sustained') or {}; f=d.get('fast_arithmetic') or {}
+print('$v $wl burst kernel_ms %.4f frac %.3f | sustained ms %.4f frac %.3f clocks %s' % (d['roofline']['kernel_ms'], d['roofline']['frac'], s.get('ms_per_step',0), s.get('frac_of_burst_peak',0), (s.get('clocks') or {}).get('sm_mhz')))
+if f: print('$v $wl FAST  burst ms %.4f frac %.3f | sustained ms %.4f frac %.3f clocks %s' % (f['ms_per_step'], f['frac'], f['sustained']['ms_per_step'], f['sustained']['frac_of_burst_peak'], f['sustained']['clocks'].get('sm_mhz')))"
   done
 done

@@ -11,6 +11,11 @@ run() {  # name, extra bench args
   echo "$name rc=$?"; tail -2 gpurun_out/r02_multi_${N}_$name.err
   python scripts/exchange_attribution.py gpurun_out/r02_trace_${N}_$name > gpurun_out/r02_attribution_${N}_$name.txt 2>&1
 }
+# the same box's first GPU alone, for the weak-scaling reference
+python bench.py --steps 50 --warmup 5 --no-cpu --no-e2e --no-others --no-sustained > gpurun_out/r02_multi_${N}_single.json 2>/dev/null
+python -c "
+import json; d=[json.loads(l) for l in open('gpurun_out/r02_multi_${N}_single.json') if l.startswith('{')][0]
+print('single GPU on this box: ms/step', round(d['ms_per_step'],4), 'value %.4e' % d['value'])"
 run loop --reducer peer
 run blocking --reducer peer --time-step host
 run nccl --reducer nccl
