@@ -26,6 +26,10 @@
 
 #include "fv_patch_kernel.cuh"
 
+#ifndef EXAHYPE_2D_WHATIF_NO_EXCHANGE
+#define EXAHYPE_2D_WHATIF_NO_EXCHANGE 0   // 1: what-if tuning build, wrong results (see march_row)
+#endif
+
 namespace exahype {
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int WPC_, int MINB_, bool DISS_ALL_, bool UNHALOED_,
@@ -216,11 +220,19 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
 #pragma unroll
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], f0[NEW][v], f0[OLD][v]);
 #pragma unroll
+#if EXAHYPE_2D_WHATIF_NO_EXCHANGE   // what-if build (WRONG results): how fast would the march be without the lane exchange?
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], f0[MID][v], f0[NEW][v]);
+#else
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], xr[v * XS], xl[v * XS]);
+#endif
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0 then axis 1 (test.cpp:78-95)
 #pragma unroll
     for (int v = 0; v < DV; ++v)
       qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q_old[v], l0[MID], l0[NEW], l0[OLD], m.dt);
+#if EXAHYPE_2D_WHATIF_NO_EXCHANGE
+    for (int v = 0; v < DV; ++v)
+      qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q_old[v], l1_mid, l0[NEW], l0[OLD], m.dt);
+#else
     {
       const T l_plus = xr[NR * XS], l_minus = xl[NR * XS];
 #pragma unroll
@@ -228,6 +240,7 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
         qc[v] = Upd::dissipation(qc[v], q[MID][v], xr[(NR + 1 + v) * XS], xl[(NR + 1 + v) * XS], l1_mid, l_plus, l_minus,
                                  m.dt);
     }
+#endif
     fv_apply_source<Phys, Upd, T>(qc, q[MID], m.dt);          // "Q_copy = Q_copy + dt*S" (families with a source term)
     if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
   }
@@ -237,6 +250,14 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
   for (int v = 0; v < DV; ++v) q_old[v] = q[MID][v];
   l1_mid = l1_new;
 
+#if EXAHYPE_2D_WHATIF_NO_EXCHANGE
+  if (inner) {
+    T keep = l1_new;
+    for (int v = 0; v < NR; ++v) keep = fv_max(keep, f1[v]);
+    lam_local = fv_max(lam_local, keep * T(1e-30));      // keep F_1 alive
+  }
+  return;
+#endif
   if (inner) {
     // ---------------------------------------------------------------- publish row r for the neighbouring lanes
     T* __restrict__ xw = m.X + (r & 1) * 32 + m.lane;

@@ -77,13 +77,15 @@ struct Fv3dPairConfig {
   static constexpr bool USE_TMA_STORE = UNHALOED && ((SEG_ELEMS * (int)sizeof(T)) % 16 == 0) &&
                                         ((SEG_PITCH * (int)sizeof(T)) % 16 == 0);
 
-  // Scratch layout of F_1 / L_1 and F_2 / L_2.  fp64 with an even record width: ONE record {F[0..NR), L} of RW values per
-  // slot, moved with 128-bit shared-memory accesses (RW/2 instead of RW instructions per record; a quarter-warp of
-  // consecutive slots at 48-byte pitch is bank-conflict free).  Otherwise component planes F[v][slot], L[slot].
-  // Same bytes either way: Rj = Fj + Lj, Rk = Fk + Lk.
+  // Scratch layout of F_1 / L_1 and F_2 / L_2: component planes F[v][slot], L[slot], 64-bit accesses (default).
+  // -DEXAHYPE_3D_REC_SCRATCH=1 (fp64, even record width) keeps ONE record {F[0..NR), L} of RW values per slot instead
+  // and moves it with 128-bit accesses: a third fewer shared-memory instructions (212 instead of 311 in the kernel), same
+  // bytes, same bits -- and measured SLOWER in every regime (C3 burst 0.3069 -> 0.3140 ms, sustained 0.351 -> 0.357, fast
+  // arithmetic 0.2944 -> 0.3005, profiles/r02_c3_variants.txt): the kernel is not issue-bound on its LDS/STS, and a
+  // 48-byte record pitch costs the wide accesses more wavefronts than the instructions it saves.  Kept as a tuning switch.
   static constexpr int RW = NR + 1;
 #ifndef EXAHYPE_3D_REC_SCRATCH
-#define EXAHYPE_3D_REC_SCRATCH 1
+#define EXAHYPE_3D_REC_SCRATCH 0
 #endif
   static constexpr bool REC = EXAHYPE_3D_REC_SCRATCH && sizeof(T) == 8 && (RW % 2 == 0);
   // per-warp shared memory

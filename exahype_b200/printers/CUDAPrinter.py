@@ -688,7 +688,12 @@ class CUDAPrinter(CodePrinter):
     def cache_directory() -> str:
         """Per-user, mode 0700: ``$EXAHYPE_B200_CACHE`` or ``~/.cache/exahype_b200/generated``."""
         d = os.environ.get("EXAHYPE_B200_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "exahype_b200", "generated")
-        os.makedirs(d, mode=0o700, exist_ok=True)
+        try:
+            os.makedirs(d, mode=0o700, exist_ok=True)
+            if not os.access(d, os.W_OK):
+                raise OSError("not writable")
+        except OSError:                       # no usable home directory: a private directory for this process
+            d = tempfile.mkdtemp(prefix="exahype_b200_generated_")
         return d
 
     def build_tag(self, extra=()) -> str:

@@ -30,7 +30,7 @@ def rt():
 
 def cfg_of(oracle, upd):
     return oracle.OracleConfig(dim=upd.dim, patch_size=upd.patch_size, halo=upd.halo_size, n_real=upd.n_real,
-                               n_aux=upd.n_aux, model=oracle.MODEL_EULER if upd.model == "euler" else oracle.MODEL_SWE,
+                               n_aux=upd.n_aux, model={"euler": oracle.MODEL_EULER, "swe": oracle.MODEL_SWE, "swe_source": oracle.MODEL_SWE_SOURCE}[upd.model],
                                diss=oracle.DISS_ALL if upd.dissipation == "all" else oracle.DISS_VAR0)
 
 
