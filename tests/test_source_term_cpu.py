@@ -66,7 +66,7 @@ def test_cuda_printer_recognises_the_source_statements(tmp_path):
     assert "::exahype::SweSourcePhysics<3, 3>" in cu.code and cu.template == "march"
     user = CUDAPrinter(S.declare(patch_size=8, device_source=True), function_name="swe_source_user")
     assert "static constexpr bool HAS_SOURCE = true;" in user.code and "user::sourceTerm(q, S);" in user.code
-    assert "static __device__ __forceinline__ T source(T qc, T s, T dt)" in user.code
+    assert "using Update = ::exahype::RusanovUpdate;" in user.code      # the declaration's update statements are the reference's
     assert user.build(directory=str(tmp_path)).lib_path                      # cross-compiles for sm_100a
     with pytest.raises(UnsupportedKernel):
         CUDAPrinter(S.declare(patch_size=8), model="swe")                    # source statements need the source family
