@@ -101,8 +101,10 @@ int validate(const exahype_fv_config* cfg) {
   if (cfg->model != EXAHYPE_MODEL_EULER && cfg->model != EXAHYPE_MODEL_SWE && cfg->model != EXAHYPE_MODEL_SWE_SOURCE)
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown model %d", cfg->model);
   if (cfg->flags & ~(EXAHYPE_FLAG_DISSIPATION_ALL | EXAHYPE_FLAG_OUTPUT_UNHALOED | EXAHYPE_FLAG_LAMBDA_ACCUMULATE |
-                     EXAHYPE_FLAG_KERNEL_CELL | EXAHYPE_FLAG_FAST_ARITHMETIC))
+                     EXAHYPE_FLAG_KERNEL_CELL | EXAHYPE_FLAG_FAST_ARITHMETIC | EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY))
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "unknown flag bits 0x%x", cfg->flags);
+  if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY) && !(cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED))
+    return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY is a form of the un-haloed output: set EXAHYPE_FLAG_OUTPUT_UNHALOED too");
   return EXAHYPE_OK;
 }
 
@@ -124,6 +126,27 @@ const exahype::FvEntry* find(const exahype_fv_config* cfg) {
 
 int variant_of(unsigned flags) {
   return ((flags & EXAHYPE_FLAG_DISSIPATION_ALL) ? 1 : 0) | ((flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) ? 2 : 0);
+}
+
+// The kernel a call runs: the shape's default one, its thread-per-cell alternative (EXAHYPE_FLAG_KERNEL_CELL), or the
+// form whose un-haloed output carries the unknowns only.  Shapes without auxiliary variables have one un-haloed layout.
+struct Picked {
+  exahype::FvLaunchFn launch;
+  exahype::FvPrepareFn prepare;
+};
+int pick(const exahype::FvEntry* e, const exahype_fv_config* cfg, Picked* out) {
+  const int var = variant_of(cfg->flags);
+  if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY) && cfg->n_aux > 0) {
+    const int da = var & 1;
+    if ((cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) || !e->unknowns_launch[da])
+      return fail(EXAHYPE_ERR_NO_INSTANTIATION, "EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY: this shape's kernel has no such output form "
+                                                "(committed for the row-marching kernel of the shallow-water families)");
+    *out = {e->unknowns_launch[da], e->unknowns_prepare[da]};
+    return EXAHYPE_OK;
+  }
+  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  *out = {alt ? e->alt_launch[var] : e->launch[var], alt ? e->alt_prepare[var] : e->prepare[var]};
+  return EXAHYPE_OK;
 }
 
 size_t elem_size(int dtype) { return dtype == EXAHYPE_DTYPE_F64 ? 8 : 4; }
@@ -196,9 +219,9 @@ int exahype_cuda_fv_launch_info(const exahype_fv_config* cfg, int64_t n_patches,
   int rc = lookup(cfg, &e);
   if (rc) return rc;
   exahype::FvLaunchInfo info;
-  const int var = variant_of(cfg->flags);
-  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_prepare[var];
-  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches);
+  Picked k;
+  if ((rc = pick(e, cfg, &k))) return rc;
+  cudaError_t err = k.prepare(&info, n_patches);
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_launch_info");
   if (grid) *grid = info.grid;
   if (block) *block = info.block;
@@ -224,9 +247,9 @@ int exahype_cuda_fv_step(const exahype_fv_config* cfg, const void* q_in, void* q
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "q_in / q_out must be 16-byte aligned (TMA bulk copies)");
   if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
     return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
-  const int var = variant_of(cfg->flags);
-  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
-  cudaError_t err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, nullptr);
+  Picked k;
+  if ((rc = pick(e, cfg, &k))) return rc;
+  cudaError_t err = k.launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, nullptr);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch");
   g_launches.fetch_add(1);
   return EXAHYPE_OK;
@@ -238,10 +261,10 @@ int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, 
   int rc = lookup(cfg, &e);
   if (rc) return rc;
   if (!reducer || !lambda_max) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "reducer / lambda_max must not be null");
-  const int var = variant_of(cfg->flags);
-  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  Picked k;
+  if ((rc = pick(e, cfg, &k))) return rc;
   exahype::FvLaunchInfo info;
-  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches > 0 ? n_patches : 1);
+  cudaError_t err = k.prepare(&info, n_patches > 0 ? n_patches : 1);
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_allreduce (launch info)");
   exahype::PeerReducer* r = static_cast<exahype::PeerReducer*>(reducer);
   if ((rc = reducer_failed(r))) return rc;
@@ -265,7 +288,7 @@ int exahype_cuda_fv_step_allreduce(const exahype_fv_config* cfg, void* reducer, 
   exahype::FvGatherRaw g = {nullptr, nullptr, nullptr, {}, nullptr, nullptr, nullptr};
   err = exahype::peer_reducer_next_fused(r, &g.peer);
   if (err != cudaSuccess) return cuda_fail(err, "peer reducer not connected, or a time loop's exchange is still pending (flush it)");
-  err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, &g);
+  err = k.launch(q_in, q_out, n_patches, dt, lambda_patch, lambda_max, s, &g);
   if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (fused all-reduce)");
   g_launches.fetch_add(1);
   return EXAHYPE_OK;
@@ -277,6 +300,8 @@ int exahype_cuda_fv_step_cell_data(const exahype_fv_config* cfg, const exahype_c
   int rc = lookup(cfg, &e);
   if (rc) return rc;
   if (!cells) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "cells is null");
+  if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY) && cfg->n_aux > 0)
+    return fail(EXAHYPE_ERR_NO_INSTANTIATION, "EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY: CellData::QOut carries the auxiliary variables");
   if (cells->n_patches < 0) return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "n_patches must be >= 0 (got %lld)", (long long)cells->n_patches);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (lambda_max && !(cfg->flags & EXAHYPE_FLAG_LAMBDA_ACCUMULATE)) {
@@ -368,7 +393,8 @@ int exahype_cuda_time_step_host(const exahype_fv_config* cfg, const void* q_host
   const size_t es = elem_size(cfg->dtype);
   const int nv = cfg->n_real + cfg->n_aux;
   const size_t in_patch = (size_t)ipow_ll(cfg->patch_size + 2 * cfg->halo, cfg->dim) * nv * es;
-  const size_t out_patch = unhaloed ? (size_t)ipow_ll(cfg->patch_size, cfg->dim) * nv * es : in_patch;
+  const int out_nv = (cfg->flags & EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY) ? cfg->n_real : nv;
+  const size_t out_patch = unhaloed ? (size_t)ipow_ll(cfg->patch_size, cfg->dim) * out_nv * es : in_patch;
 
   int dev = 0;
   cudaError_t err = cudaGetDevice(&dev);
@@ -647,10 +673,10 @@ int exahype_cuda_fv_step_time_loop(const exahype_fv_config* cfg, void* loop, con
     if ((cfg->flags & EXAHYPE_FLAG_OUTPUT_UNHALOED) && q_in == q_out)
       return fail(EXAHYPE_ERR_INVALID_ARGUMENT, "un-haloed output cannot alias the haloed input");
   }
-  const int var = variant_of(cfg->flags);
-  const bool alt = (cfg->flags & EXAHYPE_FLAG_KERNEL_CELL) && e->alt_launch[var];
+  Picked k;
+  if ((rc = pick(e, cfg, &k))) return rc;
   exahype::FvLaunchInfo info;
-  cudaError_t err = (alt ? e->alt_prepare[var] : e->prepare[var])(&info, n_patches > 0 ? n_patches : 1);
+  cudaError_t err = k.prepare(&info, n_patches > 0 ? n_patches : 1);
   if (err != cudaSuccess) return cuda_fail(err, "exahype_cuda_fv_step_time_loop (launch info)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool in_kernel = info.fused_allreduce && n_patches > 0 && exahype::peer_reducer_world(r) <= 32;
@@ -659,8 +685,7 @@ int exahype_cuda_fv_step_time_loop(const exahype_fv_config* cfg, void* loop, con
   if (err != cudaSuccess) return cuda_fail(err, "time loop: reducer not connected");
   if (n_patches > 0) {
     // dt by value is unused (the kernel reads / derives it on the device); lambda_max is the loop's accumulator
-    err = (alt ? e->alt_launch[var] : e->launch[var])(q_in, q_out, n_patches, 0.0, lambda_patch,
-                                                     exahype::time_loop_lambda_acc(l), s, &g);
+    err = k.launch(q_in, q_out, n_patches, 0.0, lambda_patch, exahype::time_loop_lambda_acc(l), s, &g);
     if (err != cudaSuccess) return cuda_fail(err, "fv_step_kernel launch (time loop)");
     g_launches.fetch_add(1);
   } else {

@@ -33,7 +33,7 @@
 namespace exahype {
 
 template <class Phys_, class Upd_, typename T_, int P_, int H_, int WPC_, int MINB_, bool DISS_ALL_, bool UNHALOED_,
-          int VEC_, int PF_ = 2, bool GATHER_ = false>
+          int VEC_, int PF_ = 2, bool GATHER_ = false, bool UNKNOWNS_ONLY_ = false>
 struct Fv2dMarchConfig {
   using Phys = Phys_;
   using Upd = Upd_;
@@ -52,7 +52,12 @@ struct Fv2dMarchConfig {
   static constexpr int NROW = P + 2;                      // rows a patch needs: one halo layer each side
   static constexpr int CELL_BYTES = NV * (int)sizeof(T);
   static constexpr int PATCH_ELEMS = S * S * NV;
-  static constexpr int OUT_PATCH_ELEMS = P * P * NV;
+  // EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY: un-haloed output without the auxiliary variables, [P][P][NR].  The step never
+  // changes them, and copying them through is 13 % of the traffic of a 32x32 shallow-water batch (ncu: 4.73 GB moved
+  // against 4.03 GB algorithmic, at the HBM wall).
+  static constexpr bool UNKNOWNS_ONLY = UNKNOWNS_ONLY_ && UNHALOED_ && (NA > 0);
+  static constexpr int OUT_NV = UNKNOWNS_ONLY ? NR : NV;
+  static constexpr int OUT_PATCH_ELEMS = P * P * OUT_NV;
   static constexpr int DV = DISS_ALL ? NR : 1;
   static constexpr int COMPS = NR + 1 + DV;               // F_1[NR], L_1, Q[DV] cross lanes
   static constexpr int NT = WPC * 32;
@@ -153,6 +158,17 @@ __device__ __forceinline__ void store_cell(typename C::T* p, const typename C::T
   }
 }
 
+// the NR unknowns of a cell into an output without auxiliary variables (cells of NR values: 24 bytes for fp64 shallow
+// water -- lanes write consecutive cells, every sector is completed inside L2 before it is written back: C4 0.718 ->
+// 0.652 ms).  Packing the row into whole 32-byte vectors through a warp-private staging row first was slower (0.683 ms:
+// three shared stores, a __syncwarp and two shared loads per row cost more than the partial sectors).  fp32 cells of 12
+// bytes in 4-byte pieces do not pay at all (C4 fp32 0.400 -> 0.416 ms), either way.
+template <class C>
+__device__ __forceinline__ void store_unknowns(typename C::T* p, const typename C::T (&q)[C::NV]) {
+#pragma unroll
+  for (int v = 0; v < C::NR; ++v) p[v] = q[v];
+}
+
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -242,7 +258,11 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
     }
 #endif
     fv_apply_source<Phys, Upd, T>(qc, q[MID], m.dt);          // "Q_copy = Q_copy + dt*S" (families with a source term)
-    if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
+    if constexpr (C::UNKNOWNS_ONLY) {
+      if (m.store_ok) store_unknowns<C>(m.out_ptr + (long long)(r - 2) * (P * NR), qc);
+    } else {
+      if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
+    }
   }
 
   // row r-1 becomes row r-2 of the next step: keep what the dissipation needs of it before its ring slot is reloaded
@@ -312,7 +332,7 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   const T* const patch_in = gather.template in<C::GATHER>(q_in, patch, C::PATCH_ELEMS);
   m.dt = gather.template step<C::GATHER>(dt, patch);
   m.row_ptr = patch_in + ((long long)(H - 1) * S + (m.k + H)) * NV;
-  m.out_ptr = C::UNHALOED ? gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + m.k * NV
+  m.out_ptr = C::UNHALOED ? gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + m.k * C::OUT_NV
                           : gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + ((long long)H * S + (m.k + H)) * NV;
   m.l2_ptr = reinterpret_cast<const unsigned char*>(patch_in + (long long)(H - 1) * S * NV);
   if (C::L2_BULK && m.k == 0) l2_prefetch_bulk(m.l2_ptr, C::L2_ROWS * C::ROW_BYTES);

@@ -26,6 +26,10 @@ struct FvEntry {
   FvPrepareFn alt_prepare[4];
   // the default kernel instantiated for the CellData form (per-patch pointers / time steps): exahype_cuda_fv_step_cell_data
   FvLaunchFn gather_launch[4];
+  // un-haloed output without the auxiliary variables (EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY), index = DISSIPATION_ALL;
+  // null when the shape's default kernel has no such form (shapes without auxiliary variables never need one)
+  FvLaunchFn unknowns_launch[2];
+  FvPrepareFn unknowns_prepare[2];
 };
 
 struct FvEntryList {
@@ -83,12 +87,14 @@ template <class Phys, typename T, int P, int H, int NG, int R, int MINB>
 struct March3dFamily {
   template <bool DA, bool UH> using Dense = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, false>>;
   template <bool DA, bool UH> using Gather = Fv3dMarchLauncher<Fv3dMarchConfig<Phys, RusanovUpdate, T, P, H, NG, R, MINB, DA, UH, true>>;
+  static constexpr bool HAS_UNKNOWNS = false;
 };
 // 3-D warp-per-patch marching (8x8x8 patches): NW warps per CTA, ring of R planes per warp
 template <class Phys, typename T, int P, int H, int NW, int R, int SB = 2>
 struct Pair3dFamily {
   template <bool DA, bool UH> using Dense = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, false, SB>>;
   template <bool DA, bool UH> using Gather = Fv3dPairLauncher<Fv3dPairConfig<Phys, RusanovUpdate, T, P, H, NW, R, DA, UH, true, SB>>;
+  static constexpr bool HAS_UNKNOWNS = false;
 };
 // 2-D row marching: WPC warps per CTA, MINB CTAs per SM, PF rows of register prefetch
 template <class Phys, typename T, int P, int H, int WPC, int MINB, int PF>
@@ -99,7 +105,20 @@ struct March2dFamily {
                                   Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, UH, NARROW, PF, false>>;
   template <bool DA, bool UH>
   using Gather = Fv2dMarchLauncher<Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, UH, NARROW, PF, true>>;
+  template <bool DA>
+  using Unknowns = Fv2dMarchDispatch<Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, true, WIDE, PF, false, true>,
+                                     Fv2dMarchConfig<Phys, RusanovUpdate, T, P, H, WPC, MINB, DA, true, NARROW, PF, false, true>>;
+  static constexpr bool HAS_UNKNOWNS = Phys::NA > 0;
 };
+template <class March>
+inline void add_unknowns_form(FvEntry& e) {
+  if constexpr (March::HAS_UNKNOWNS) {
+    e.unknowns_launch[0] = &March::template Unknowns<false>::launch;
+    e.unknowns_launch[1] = &March::template Unknowns<true>::launch;
+    e.unknowns_prepare[0] = &March::template Unknowns<false>::prepare;
+    e.unknowns_prepare[1] = &March::template Unknowns<true>::prepare;
+  }
+}
 
 // one kernel for the shape (thread per cell)
 template <class Cell>
@@ -109,13 +128,17 @@ inline FvEntry cell_entry(int model, int dtype, int dim, int P, int H, int nr, i
 // marching kernel by default, thread-per-cell kernel behind EXAHYPE_FLAG_KERNEL_CELL
 template <class March, class Cell>
 inline FvEntry march_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
-  return make_entry<March::template Dense, March::template Gather, Cell::template Dense>(model, dtype, dim, P, H, nr, na);
+  FvEntry e = make_entry<March::template Dense, March::template Gather, Cell::template Dense>(model, dtype, dim, P, H, nr, na);
+  add_unknowns_form<March>(e);
+  return e;
 }
 
 // marching kernel only (no thread-per-cell alternative: the shape's tile does not fit shared memory, or none is wanted)
 template <class March>
 inline FvEntry march_only_entry(int model, int dtype, int dim, int P, int H, int nr, int na) {
-  return make_entry<March::template Dense, March::template Gather, NoKernel>(model, dtype, dim, P, H, nr, na);
+  FvEntry e = make_entry<March::template Dense, March::template Gather, NoKernel>(model, dtype, dim, P, H, nr, na);
+  add_unknowns_form<March>(e);
+  return e;
 }
 
 }  // namespace exahype

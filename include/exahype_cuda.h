@@ -67,7 +67,15 @@ enum {
    * bound BASELINE.json states -- but are no longer bitwise equal to it.  Committed for the headline shapes (8^3 Euler
    * fp64, 16^2 Euler fp64, 32^2 shallow water fp64 / fp32); other shapes keep the reference arithmetic.  The kernels
    * execute ~14 % fewer instructions, which is what bounds them once the board runs power-limited. */
-  EXAHYPE_FLAG_FAST_ARITHMETIC = 1u << 4
+  EXAHYPE_FLAG_FAST_ARITHMETIC = 1u << 4,
+  /* With EXAHYPE_FLAG_OUTPUT_UNHALOED: q_out carries the unknowns only, q_out[patch][P]^dim[n_real].  The step never
+   * changes the auxiliary variables (every update statement of the reference runs over the unknowns, "Unit test/
+   * test.cpp":60-95; the copy-back at :96-103 passes the auxiliary values through as they came in), and an
+   * un-haloed QOut that repeats them costs their bytes a second time: 13 % of the DRAM traffic of a 32x32 shallow-water
+   * batch, which runs at the HBM wall.  No effect for n_aux == 0.  Committed for the row-marching kernel of the
+   * shallow-water families (dense batches: exahype_cuda_fv_step / _allreduce / _time_loop); EXAHYPE_ERR_NO_INSTANTIATION
+   * elsewhere. */
+  EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY = 1u << 5
 };
 
 typedef struct {

@@ -52,6 +52,9 @@ def test_argument_validation_mirrors_viable(lib):
     assert rc(halo=-1) == -1
     assert rc(halo=0) == -1
     assert rc(flags=1 << 9) == -1
+    # the unknowns-only output is a form of the un-haloed one
+    assert rc(flags=runtime.FLAG_OUTPUT_UNKNOWNS_ONLY) == -1 and b"UNHALOED" in lib.exahype_cuda_last_error()
+    assert rc(flags=runtime.FLAG_OUTPUT_UNKNOWNS_ONLY | runtime.FLAG_OUTPUT_UNHALOED) == 0
     assert rc(patch_size=7) == -2 and b"CUDAPrinter" in lib.exahype_cuda_last_error()
     assert rc() == 0                      # zero patches: nothing to do, no device needed
     with pytest.raises(Exception, match="viability"):

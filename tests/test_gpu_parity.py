@@ -62,7 +62,7 @@ def gpu_step(torch, upd, q_np, dt, out=None, want_lambda=True):
     raw_l, lam = guarded(torch, (n,), tdt, -1.0)
     raw_m, lmax = guarded(torch, (1,), tdt, -1.0)
     raws = [raw_q, raw_l, raw_m]
-    if upd.output == "unhaloed":
+    if upd.output in ("unhaloed", "unknowns"):
         raw_o, out = guarded(torch, upd.out_shape(n), tdt, 7.0)
         raws.append(raw_o)
     res = upd.step(q, out, dt, lam if want_lambda else None, lmax if want_lambda else None)
@@ -265,6 +265,55 @@ def test_row_marching_on_16_byte_aligned_buffers(torch, rt, oracle, model, P, nr
         assert_bitwise(lam.cpu().numpy(), lam_o, "lambda")
 
 
+def _with_aux():
+    return [s for s in _committed() if s[5] > 0 and s[2] in (16, 32)]      # shapes the row-marching kernel serves
+
+
+@pytest.mark.parametrize("shape", _with_aux(), ids=lambda s: "-".join(map(str, s)))
+@pytest.mark.parametrize("diss", ["var0", "all"])
+def test_unknowns_only_output_matches_oracle_bitwise(torch, rt, oracle, shape, diss):
+    """EXAHYPE_FLAG_OUTPUT_UNKNOWNS_ONLY: q_out[patch][P][P][n_real] holds exactly the unknowns of the un-haloed output
+    (the auxiliary variables, which a step never changes, are not repeated), on 32- and 16-byte aligned buffers, for a
+    ragged batch; the thread-per-cell kernel and the CellData form have no such output and say so."""
+    model, dim, P, h, nr, na, dtype = shape
+    upd = rt.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output="unknowns")
+    assert upd.out_shape(5) == (5, P, P, nr)
+    cfg = oracle_cfg(oracle, upd)
+    npdt = np.float64 if dtype == "f64" else np.float32
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    n = 3 * upd.launch_info(10 ** 6)["patches_per_tile"] * 5 + 1
+    q0 = oracle.fill_synthetic(cfg, n, dtype=npdt)
+    want = q0.copy()
+    lam_o, lmax_o = oracle.step(cfg, want, 0.01, nthreads=4)
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.01)
+    assert got.shape == upd.out_shape(n)
+    assert_bitwise(got, interior(upd, want)[..., :nr], "unknowns")
+    assert_bitwise(lam, lam_o, "lambda_patch")
+    assert lmax == float(lmax_o)
+    # 16-byte aligned buffers take the 128-bit loads
+    off = 16 // q0.itemsize
+    raw_in = torch.zeros(q0.size + off, dtype=tdt, device="cuda")
+    q = raw_in[off:].view(q0.shape); q.copy_(torch.from_numpy(q0))
+    raw_out = torch.full((int(np.prod(upd.out_shape(n))) + off,), 7.0, dtype=tdt, device="cuda")
+    out = raw_out[off:].view(upd.out_shape(n))
+    upd.step(q, out, 0.01)
+    torch.cuda.synchronize()
+    assert_bitwise(out.cpu().numpy(), interior(upd, want)[..., :nr], "unknowns, 16-byte aligned")
+    with pytest.raises(rt.ExaHyPECudaError) as e:
+        dataclasses.replace(upd, kernel="cell").step(q, out, 0.01)
+    assert e.value.code == -2
+
+
+def test_unknowns_only_output_is_the_unhaloed_one_without_auxiliary_variables(torch, rt, oracle):
+    """No auxiliary variables, no second layout: the flag is accepted and changes nothing (3-D Euler, 8^3)."""
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0, output="unknowns")
+    cfg = oracle_cfg(oracle, upd)
+    q0 = oracle.fill_synthetic(cfg, 41)
+    want = q0.copy(); oracle.step(cfg, want, 0.01)
+    got, _, _ = gpu_step(torch, upd, q0, 0.01)
+    assert_bitwise(got, interior(upd, want), "unknowns == unhaloed")
+
+
 # ----------------------------------------------------------------------------------------- semantics of the boundary
 def test_out_of_place_haloed_writes_interior_only(torch, rt, oracle):
     upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0)
@@ -393,17 +442,20 @@ def test_cell_data_form_gathered_patches_and_per_patch_dt(torch, rt, oracle, mod
 
 
 # ----------------------------------------------------------------------------------------- BASELINE sizes
-@pytest.mark.parametrize("model,dim,P,nr,na,n", [("euler", 3, 8, 5, 0, 32768), ("euler", 2, 16, 4, 0, 65536),
-                                                 ("swe", 2, 32, 3, 1, 16384)])
-def test_full_size_properties(torch, rt, oracle, model, dim, P, nr, na, n):
+@pytest.mark.parametrize("model,dim,P,nr,na,n,dtype", [
+    ("euler", 3, 8, 5, 0, 32768, "f64"), ("euler", 2, 16, 4, 0, 65536, "f64"),
+    ("swe", 2, 32, 3, 1, 65536, "f64"), ("swe", 2, 32, 3, 1, 65536, "f32")])      # C3, C2, C4, C4 fp32 as benched
+def test_full_size_properties(torch, rt, oracle, model, dim, P, nr, na, n, dtype):
     """At the full BASELINE batch sizes: determinism, shard-independence (what multi-GPU relies on), untouched
-    halos, lambda_max == max(lambda_patch), and bitwise parity on the first / last / middle patches."""
-    upd = rt.PatchUpdate(model, dim, P, 1, nr, na)
+    halos, lambda_max == max(lambda_patch), and bitwise parity on the first / last / middle patches (fp32 against
+    the fp32 oracle)."""
+    upd = rt.PatchUpdate(model, dim, P, 1, nr, na, dtype=dtype)
     cfg = oracle_cfg(oracle, upd)
-    q0 = oracle.fill_synthetic(cfg, n)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    q0 = oracle.fill_synthetic(cfg, n, dtype=np.float64 if dtype == "f64" else np.float32)
     q = torch.from_numpy(q0).cuda()
-    lam = torch.zeros(n, dtype=torch.float64, device="cuda")
-    lmax = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lam = torch.zeros(n, dtype=tdt, device="cuda")
+    lmax = torch.zeros(1, dtype=tdt, device="cuda")
     a = q.clone(); upd.step(a, None, 0.01, lam, lmax)
     b = q.clone(); upd.step(b, None, 0.01)
     assert torch.equal(a, b)

@@ -189,7 +189,11 @@ def test_fp32_oracle_tracks_fp64(oracle):
     oracle.step(cfg, q64, 0.01)
     oracle.step(cfg, q32, 0.01)
     assert np.array_equal(q64[..., 3], bathy)
-    np.testing.assert_allclose(q32, q64, rtol=2e-5, atol=2e-6)
+    # the ONE stated fp32 bound (tests/test_gpu_parity.py): max-norm, per variable,
+    # max |q32 - q64| <= 2e-6 * max |q64|
+    scale = np.abs(q64).reshape(-1, 4).max(axis=0)
+    err = np.abs(q32.astype(np.float64) - q64).reshape(-1, 4).max(axis=0)
+    assert (err <= 2e-6 * scale).all(), err / scale
 
 
 def test_rejects_invalid_configurations(oracle):
