@@ -86,6 +86,14 @@ struct Fv2dMarchConfig {
 
   // warp-private exchange area: [COMPS][XS] values; slots [0,32) row buffer 0, [32,64) row buffer 1,
   // [64,96) left face-halo table (patch of the warp, row), [96,128) right face-halo table
+  // CellData form: the patches come through per-patch pointers whose alignment the launcher cannot see (the pointer
+  // arrays live in device memory).  Each lane looks at ITS patch's pointers and takes the 256-bit access when they
+  // are 32-byte aligned, the two 128-bit ones otherwise (per-lane branch, divergent only inside a warp whose patches
+  // differ): gathered C2 on aligned patches 0.272 -> see profiles/README.md.
+#ifndef EXAHYPE_2D_GATHER_DYN_WIDE
+#define EXAHYPE_2D_GATHER_DYN_WIDE 1
+#endif
+  static constexpr bool DYN_WIDE = EXAHYPE_2D_GATHER_DYN_WIDE && GATHER && VEC == 16 && sizeof(T) == 8 && CELL_BYTES % 32 == 0;
   static constexpr int XS = 128;
   static constexpr int WARP_BYTES = COMPS * XS * (int)sizeof(T);
   static constexpr int SMEM_BYTES = WPC * WARP_BYTES;
@@ -169,6 +177,34 @@ __device__ __forceinline__ void store_unknowns(typename C::T* p, const typename 
   for (int v = 0; v < C::NR; ++v) p[v] = q[v];
 }
 
+// CellData form (C::DYN_WIDE): the vector width follows the alignment of this lane's patch
+template <class C>
+__device__ __forceinline__ void load_cell(const typename C::T* p, typename C::T (&q)[C::NV], bool wide) {
+  if constexpr (C::DYN_WIDE) {
+    if (wide) {
+#pragma unroll
+      for (int v = 0; v < C::NV; v += 4)
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(q[v]), "=d"(q[v + 1]), "=d"(q[v + 2]), "=d"(q[v + 3]) : "l"(p + v));
+      return;
+    }
+  }
+  load_cell<C>(p, q);
+}
+template <class C>
+__device__ __forceinline__ void store_cell(typename C::T* p, const typename C::T (&q)[C::NV], bool wide) {
+  if constexpr (C::DYN_WIDE) {
+    if (wide) {
+#pragma unroll
+      for (int v = 0; v < C::NV; v += 4)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + v), "d"(q[v]), "d"(q[v + 1]), "d"(q[v + 2]),
+                     "d"(q[v + 3]) : "memory");
+      return;
+    }
+  }
+  store_cell<C>(p, q);
+}
+
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -185,6 +221,7 @@ struct RowMarch {
   int lane, k;
   int halo_slot_left, halo_slot_right;   // 64 + sub*P, 96 + sub*P (+ interior row)
   bool store_ok;
+  bool wide_in, wide_out;    // C::DYN_WIDE: this lane's patch is 32-byte aligned (input / output)
 };
 
 // One row of the march.  SLOT = r & 3 at compile time; r itself is a run-time (warp-uniform) value.
@@ -206,7 +243,7 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
   static_assert(PRE == OLD, "the prefetched row takes the ring slot of row r-2");
 
   // row r+PF -> the ring slot that held row r-2 (whose dissipated variables were saved to q_old last step)
-  if (r + PF < C::NROW) load_cell<C>(m.row_ptr + (long long)(r + PF) * (C::S * NV), q[PRE]);
+  if (r + PF < C::NROW) load_cell<C>(m.row_ptr + (long long)(r + PF) * (C::S * NV), q[PRE], m.wide_in);
   if (C::L2_BULK && C::L2_ROWS < C::NROW && m.k == 0 && r + C::L2_ROWS < C::NROW)
     l2_prefetch_bulk(m.l2_ptr + (long long)(r + C::L2_ROWS) * C::ROW_BYTES, C::ROW_BYTES);
 
@@ -261,7 +298,7 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
     if constexpr (C::UNKNOWNS_ONLY) {
       if (m.store_ok) store_unknowns<C>(m.out_ptr + (long long)(r - 2) * (P * NR), qc);
     } else {
-      if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc);
+      if (m.store_ok) store_cell<C>(m.out_ptr + (long long)(r - 2) * ((C::UNHALOED ? P : C::S) * NV), qc, m.wide_out);
     }
   }
 
@@ -335,6 +372,9 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   m.out_ptr = C::UNHALOED ? gather.template out<C::GATHER>(q_out, patch, C::OUT_PATCH_ELEMS) + m.k * C::OUT_NV
                           : gather.template out<C::GATHER>(q_out, patch, C::PATCH_ELEMS) + ((long long)H * S + (m.k + H)) * NV;
   m.l2_ptr = reinterpret_cast<const unsigned char*>(patch_in + (long long)(H - 1) * S * NV);
+  // cells are 32 bytes and rows a whole number of cells: a 32-byte aligned patch has 32-byte aligned cells throughout
+  m.wide_in = C::DYN_WIDE && (reinterpret_cast<uintptr_t>(patch_in) & 31) == 0;
+  m.wide_out = C::DYN_WIDE && (reinterpret_cast<uintptr_t>(m.out_ptr) & 31) == 0;
   if (C::L2_BULK && m.k == 0) l2_prefetch_bulk(m.l2_ptr, C::L2_ROWS * C::ROW_BYTES);
 
   T q[C::RING][NV], f0[C::RING][NR], l0[C::RING], l1_mid = T(0), q_old[DV], lam_local = T(0);
@@ -351,14 +391,14 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
 
   // rows 0..PF-1 of the march are requested first, the face-halo cells behind them
 #pragma unroll
-  for (int w = 0; w < C::PF; ++w) load_cell<C>(m.row_ptr + w * (S * NV), q[w]);
+  for (int w = 0; w < C::PF; ++w) load_cell<C>(m.row_ptr + w * (S * NV), q[w], m.wide_in);
 
   {
     // ------------------------------------------------------------------ face-halo table: lane <-> (patch, interior row)
     const T* left = patch_in + ((long long)(m.k + H) * S + (H - 1)) * NV;   // row = m.k of this lane's own patch
     T ql[NV], qr[NV];
-    load_cell<C>(left, ql);
-    load_cell<C>(left + (P + 1) * NV, qr);
+    load_cell<C>(left, ql, m.wide_in);
+    load_cell<C>(left + (P + 1) * NV, qr, m.wide_in);
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       const T(&qh)[NV] = side ? qr : ql;
@@ -447,14 +487,14 @@ struct Fv2dMarchDispatch {
   }
 };
 
-// what a generated unit (exahype.printers.CUDAPrinter) instantiates: 4 warps per CTA, dispatch on buffer alignment
+// what a generated unit (exahype.printers.CUDAPrinter) instantiates: one warp per CTA (inst_euler2d.cu), dispatch on buffer alignment
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH>
 using Fv2dMarchAuto =
-    Fv2dMarchDispatch<Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::WIDE>,
-                      Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW>>;
+    Fv2dMarchDispatch<Fv2dMarchConfig<Phys, Upd, T, P, H, 1, 16, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::WIDE>,
+                      Fv2dMarchConfig<Phys, Upd, T, P, H, 1, 16, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW>>;
 // CellData form: gathered patches are only known to be 16-byte aligned individually -> narrow accesses
 template <class Phys, class Upd, typename T, int P, int H, bool DA, bool UH, int PF = 2>
 using Fv2dMarchGather =
-    Fv2dMarchLauncher<Fv2dMarchConfig<Phys, Upd, T, P, H, 4, 4, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW, PF, true>>;
+    Fv2dMarchLauncher<Fv2dMarchConfig<Phys, Upd, T, P, H, 1, 16, DA, UH, Fv2dVec<T, Phys::NR + Phys::NA>::NARROW, PF, true>>;
 
 }  // namespace exahype

@@ -31,9 +31,9 @@ constexpr int EU = EXAHYPE_MODEL_EULER, SWE = EXAHYPE_MODEL_SWE, F64 = EXAHYPE_D
 const std::vector<FvEntry>& entries() {
   static const std::vector<FvEntry> v = {
       march_only_entry<Pair3dFamily<E3, double, 8, 1, EXAHYPE_FAST_3D_NW, EXAHYPE_FAST_3D_PR, EXAHYPE_FAST_3D_SB>>(EU, F64, 3, 8, 1, 5, 0),   // C3 / C5
-      march_only_entry<March2dFamily<E2, double, 16, 1, 4, 4, 2>>(EU, F64, 2, 16, 1, 4, 0),                                 // C2
-      march_only_entry<March2dFamily<SW, double, 32, 1, 4, 4, 3>>(SWE, F64, 2, 32, 1, 3, 1),                                // C4
-      march_only_entry<March2dFamily<SW, float, 32, 1, 4, 6, 4>>(SWE, F32, 2, 32, 1, 3, 1),                                 // C4 fp32 (contraction only)
+      march_only_entry<March2dFamily<E2, double, 16, 1, 1, 16, 2>>(EU, F64, 2, 16, 1, 4, 0),                                 // C2
+      march_only_entry<March2dFamily<SW, double, 32, 1, 1, 16, 3>>(SWE, F64, 2, 32, 1, 3, 1),                                // C4
+      march_only_entry<March2dFamily<SW, float, 32, 1, 1, 24, 4>>(SWE, F32, 2, 32, 1, 3, 1),                                 // C4 fp32 (contraction only)
   };
   return v;
 }

@@ -441,6 +441,49 @@ def test_cell_data_form_gathered_patches_and_per_patch_dt(torch, rt, oracle, mod
         assert_bitwise(pool.cpu().numpy()[slots], q0, "QIn untouched")
 
 
+@pytest.mark.parametrize("model,P,nr,na", [("euler", 16, 4, 0), ("swe", 32, 3, 1), ("euler", 8, 4, 0)])
+@pytest.mark.parametrize("output", ["haloed", "unhaloed"])
+def test_cell_data_form_mixed_patch_alignment(torch, rt, oracle, model, P, nr, na, output):
+    """The gathered row-marching kernel picks 256-bit or 128-bit accesses per lane from the alignment of that lane's
+    patch: a pool whose slots alternate between 32-byte and 16-byte alignment, permuted, so that the patches of one warp
+    differ -- every patch still equals the oracle bit for bit and nothing else in the pool changes."""
+    upd = rt.PatchUpdate(model, 2, P, 1, nr, na, output=output)
+    cfg = oracle_cfg(oracle, upd)
+    n, pool_n = 75, 96
+    rng = np.random.default_rng(11)
+    slots = rng.permutation(pool_n)[:n]
+    q0 = oracle.fill_synthetic(cfg, n)
+    per_in = int(np.prod(upd.in_shape(1)))
+    stride_in = per_in + 2                                   # 16 bytes of padding: odd slots are 16-byte aligned only
+    pool = torch.full((pool_n * stride_in,), -5.0, dtype=torch.float64, device="cuda")
+    assert pool.data_ptr() % 32 == 0 and (per_in * 8) % 32 == 0
+    for p, s_ in enumerate(slots):
+        pool[s_ * stride_in:s_ * stride_in + per_in] = torch.from_numpy(q0[p].ravel()).cuda()
+    in_ptrs = torch.tensor([pool.data_ptr() + int(s_) * stride_in * 8 for s_ in slots], dtype=torch.int64, device="cuda")
+    assert len({int(x) % 32 for x in in_ptrs.tolist()}) == 2
+    if output == "haloed":
+        out_pool, out_ptrs, per_out, stride_out, out_slots = pool, in_ptrs, per_in, stride_in, slots
+    else:
+        per_out = int(np.prod(upd.out_shape(1)))
+        stride_out = per_out + 2
+        out_slots = rng.permutation(pool_n)[:n]
+        out_pool = torch.full((pool_n * stride_out,), -7.0, dtype=torch.float64, device="cuda")
+        out_ptrs = torch.tensor([out_pool.data_ptr() + int(s_) * stride_out * 8 for s_ in out_slots], dtype=torch.int64, device="cuda")
+    lam = torch.zeros(n, dtype=torch.float64, device="cuda")
+    upd.step_cell_data(in_ptrs, out_ptrs, dt=0.01, max_eigenvalue=lam)
+    torch.cuda.synchronize()
+    want = q0.copy()
+    lam_o, _ = oracle.step(cfg, want, 0.01, nthreads=4)
+    assert_bitwise(lam.cpu().numpy(), lam_o, "maxEigenvalue")
+    out_np = out_pool.cpu().numpy().reshape(pool_n, stride_out)
+    fill = -5.0 if output == "haloed" else -7.0
+    assert (out_np[:, per_out:] == fill).all(), "padding between the slots"
+    expect = want if output == "haloed" else interior(upd, want)
+    assert_bitwise(out_np[out_slots, :per_out].reshape(expect.shape), expect, "gathered patches")
+    untouched = np.setdiff1d(np.arange(pool_n), out_slots)
+    assert (out_np[untouched] == fill).all()
+
+
 # ----------------------------------------------------------------------------------------- BASELINE sizes
 @pytest.mark.parametrize("model,dim,P,nr,na,n,dtype", [
     ("euler", 3, 8, 5, 0, 32768, "f64"), ("euler", 2, 16, 4, 0, 65536, "f64"),
