@@ -16,12 +16,17 @@
 //   * only F_1, L_1 and the DV dissipated variables of the row cross lanes, through a warp-private double-buffered
 //     shared row (conflict-free SoA, one __syncwarp per row; no CTA barriers, no mbarriers, no named barriers).
 //   * the 2*P face-halo cells of axis 1 of each patch (one layer left and right of every interior row) are evaluated
-//     32 at a time before the march (lane <-> (patch, row)) into a warp-private table that the edge lanes read instead
-//     of the shared row.  Halo corners are never touched (they are not inputs).
+//     32 at a time (lane <-> (patch, row)) into a warp-private table that the edge lanes read instead of the shared
+//     row: requested at the start, evaluated behind rows 0 and 1 of the march.  Halo corners are never touched (they
+//     are not inputs).
 //   * per-patch max eigenvalue: running maximum in registers, segmented warp-shuffle reduction at the end of the patch.
 //
+//   * ONE warp per CTA: a CTA's slot is handed to the next CTA only when its last warp is done (inst_euler2d.cu).
+//
 // Shared memory: COMPS * 128 values per warp (6 KB for Euler fp64 var0), 128 registers: 16 independent warps per SM, each
-// streaming rows of 512-1024 contiguous bytes.  Measured: C2 0.22 ms, C4 0.72 ms (83-86 % of the measured HBM copy peak).
+// streaming rows of 512-1024 contiguous bytes.  Measured (round 2): C2 0.206 ms = 0.89-0.90 of the measured HBM copy
+// peak, C4 0.72 ms = 0.855 (0.65 ms = 0.94-0.96 when the un-haloed output does not repeat the auxiliary variable:
+// UNKNOWNS_ONLY), C4 fp32 0.369 ms = 0.834.
 #pragma once
 
 #include "fv_patch_kernel.cuh"
@@ -74,6 +79,7 @@ struct Fv2dMarchConfig {
   // Small patches (all their rows within EXAHYPE_2D_L2_WHOLE bytes: 16x16 fp64 is 10 KB) are requested whole by one
   // prefetch before the march: no per-row prefetch instructions at all (C2 0.2152 -> 0.2136 ms); the eviction argument
   // above concerns the 37 KB patches, which keep the short window.
+  // (one request per row: 2 / 4 / 8 rows per request, or a 4 KB window, changed nothing or lost 1-3 % on 32x32 patches)
 #ifndef EXAHYPE_2D_L2_WHOLE
 #define EXAHYPE_2D_L2_WHOLE 12288
 #endif
@@ -336,6 +342,17 @@ __device__ __forceinline__ bool march_ring(const RowMarch<C>& m, int& r, A&... a
   else return false;
 }
 
+// One warp = one unit of PPW patches; the grid covers the batch and the hardware hands a finished CTA's slot to the next
+// one.  Order inside a unit: L2 prefetch, rows 0..PF-1, face-halo cells requested; rows 0 and 1 of the march (they need
+// nothing but the rows already there); face-halo table; the rest of the march.
+//
+// Measured and dropped (profiles/r02_2d_persistent_ab.txt, all bitwise equal): a PERSISTENT grid of resident warps --
+// units dealt round robin (C2 0.205 -> 0.241 ms) or claimed from a counter (0.228 ms), with or without the march's
+// last rows loading the next unit's first rows into the free ring slots (0.250 / 0.241 ms: pipelining across units
+// made it slower still), or asking for the next unit's head by L2 prefetch.  A fresh CTA that requests its whole patch
+// with ONE bulk prefetch and then sits out the DRAM latency (14 % of all warp samples) leaves the memory system with
+// long contiguous requests; these kernels run at 85-90 % of the copy peak, where the request pattern is worth more than
+// the hidden latency.
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
@@ -345,6 +362,7 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
   using Phys = typename C::Phys;
   using Bits = typename FloatBits<T>::type;
   constexpr int P = C::P, H = C::H, S = C::S, NV = C::NV, NR = C::NR, DV = C::DV, XS = C::XS, PPW = C::PPW;
+  static_assert(C::NROW > C::RING && C::RING >= 3, "the march is longer than its ring");
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,16 +407,20 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
 #pragma unroll
   for (int v = 0; v < DV; ++v) q_old[v] = T(0);
 
-  // rows 0..PF-1 of the march are requested first, the face-halo cells behind them
+  // rows 0..PF-1 of the march are requested first, the face-halo cells (lane <-> (patch, interior row)) behind them
 #pragma unroll
   for (int w = 0; w < C::PF; ++w) load_cell<C>(m.row_ptr + w * (S * NV), q[w], m.wide_in);
+  const T* left = patch_in + ((long long)(m.k + H) * S + (H - 1)) * NV;       // row = m.k of this lane's own patch
+  T ql[NV], qr[NV];
+  load_cell<C>(left, ql, m.wide_in);
+  load_cell<C>(left + (P + 1) * NV, qr, m.wide_in);
 
+  // ------------------------------------------------------------------ the march: rows 0..P+1, ring index = row % RING.
+  // Rows 0 and 1 come before the face-halo table (first read at row 2): C2 0.2107 -> 0.2065 ms.
+  march_row<C, 0>(m, 0, q, f0, l0, l1_mid, q_old, lam_local);
+  march_row<C, 1>(m, 1, q, f0, l0, l1_mid, q_old, lam_local);
   {
-    // ------------------------------------------------------------------ face-halo table: lane <-> (patch, interior row)
-    const T* left = patch_in + ((long long)(m.k + H) * S + (H - 1)) * NV;   // row = m.k of this lane's own patch
-    T ql[NV], qr[NV];
-    load_cell<C>(left, ql, m.wide_in);
-    load_cell<C>(left + (P + 1) * NV, qr, m.wide_in);
+    // ---------------------------------------------------------------- face-halo table
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       const T(&qh)[NV] = side ? qr : ql;
@@ -414,10 +436,9 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
     }
     __syncwarp();
   }
-
-  // ------------------------------------------------------------------ the march: rows 0..P+1, ring index = row % RING
-  int r = 0;
-  while (!march_ring<C, 0>(m, r, q, f0, l0, l1_mid, q_old, lam_local)) {}
+  int r = 2;
+  if (!march_ring<C, 2>(m, r, q, f0, l0, l1_mid, q_old, lam_local))
+    while (!march_ring<C, 0>(m, r, q, f0, l0, l1_mid, q_old, lam_local)) {}
 
   // ------------------------------------------------------------------ max eigenvalue of the input state
   T lam = lam_local;
@@ -449,6 +470,7 @@ struct Fv2dMarchLauncher {
       cached_ctas_per_sm[dev] = per_sm;
     }
     const long long units = (n_patches + C::PPW - 1) / C::PPW;
+    if ((units + C::WPC - 1) / C::WPC > 0x7fffffffll) return cudaErrorInvalidValue;     // more CTAs than a grid holds
     info->grid = (int)((units + C::WPC - 1) / C::WPC);
     info->block = C::NT;
     info->smem_bytes = C::SMEM_BYTES;
