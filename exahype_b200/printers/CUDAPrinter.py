@@ -418,6 +418,49 @@ class _DevicePrinter(C99CodePrinter):
             out = f"::exahype::fv_max<T>({out}, {a})"
         return out
 
+    # the two opaque operations of strength_reduce() (SymPy routes every undefined function through this method)
+    def _print_AppliedUndef(self, expr):
+        name = expr.func.__name__
+        if name == "exahype_recip":
+            return f"(T(1.0)/({self._print(expr.args[0])}))"
+        if name == "exahype_sqrt":
+            return f"::exahype::fv_sqrt<T>({self._print(expr.args[0])})"
+        return super()._print_Function(expr)
+
+
+_RECIP = sympy.Function("exahype_recip")
+_SQRT = sympy.Function("exahype_sqrt")
+_HALF = sympy.Rational(1, 2)
+
+
+def strength_reduce(expr):
+    """Fewer divisions and roots in a SymPy-declared functor, within the 1e-12 contract of generated kernels.
+
+    SymPy canonicalises ``sqrt(g*|p|/|rho|)`` to ``sqrt(g)*sqrt(|p|)/sqrt(|rho|)`` and keeps ``1/rho`` and ``1/|rho|`` apart: written
+    out, a cell pays two reciprocals, two roots and a division where the hand-written family pays one reciprocal and one
+    root.  Here every product's half-power factors are gathered under ONE root again (valid because SymPy only splits
+    non-negative radicands) and ``1/|x|`` becomes ``|1/x|`` (exact: the IEEE reciprocal is sign-symmetric), both as opaque
+    functions so that SymPy does not undo them and the common-subexpression pass shares ``1/rho`` between flux and
+    eigenvalue."""
+    def roots(e):
+        if isinstance(e, sympy.Pow) and e.exp == _HALF:
+            return _SQRT(e.base)
+        if isinstance(e, sympy.Pow) and e.exp == -_HALF:
+            return _SQRT(sympy.Pow(e.base, -1))
+        if isinstance(e, sympy.Mul):
+            rs = [a for a in e.args if isinstance(a, _SQRT)]
+            if len(rs) > 1:
+                rest = [a for a in e.args if not isinstance(a, _SQRT)]
+                return sympy.Mul(*rest) * _SQRT(sympy.Mul(*[a.args[0] for a in rs]))
+        return e
+    expr = sympy.sympify(expr).replace(lambda e: isinstance(e, (sympy.Pow, sympy.Mul)), roots)
+
+    def recip(e):
+        if isinstance(e.base, sympy.Abs):
+            return sympy.Abs(_RECIP(e.base.args[0]))
+        return _RECIP(e.base)
+    return expr.replace(lambda e: isinstance(e, sympy.Pow) and e.exp == -1, recip)
+
 
 def plan_symbolic_functors(groups: "Dict[tuple, list]"):
     """Common-subexpression plan for SymPy-bodied functors.
@@ -433,14 +476,15 @@ def plan_symbolic_functors(groups: "Dict[tuple, list]"):
     Returns ``(prims_lines, stored, bodies)``: assignments computing the stored temporaries (with everything they depend
     on), the stored symbols in struct order, and per group ``(local assignments, reduced expressions)``."""
     keys = list(groups)
-    flat = [e for k in keys for e in groups[k]]
+    flat = [strength_reduce(e) for k in keys for e in groups[k]]
     repl, reduced = sympy.cse(flat, symbols=sympy.numbered_symbols("cse_t"), order="none")
     defs = dict(repl)
     order = [sym for sym, _ in repl]
     temps = set(order)
 
     def expensive(expr) -> bool:
-        if any(isinstance(a, sympy.Pow) and not (a.exp.is_Integer and a.exp > 0) for a in sympy.preorder_traversal(expr)):
+        if any((isinstance(a, sympy.Pow) and not (a.exp.is_Integer and a.exp > 0)) or isinstance(a, (_RECIP, _SQRT))
+               for a in sympy.preorder_traversal(expr)):
             return True
         return bool(sympy.count_ops(expr) > 2)
     costly = {t for t in order if expensive(defs[t])}

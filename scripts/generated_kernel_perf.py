@@ -93,7 +93,7 @@ def main():
         gb = upd.algorithmic_bytes_per_patch * batch / 1e9
         flux, eig = euler_bodies(dim)
         for label, kw in (("generated, committed functor family (model='euler')", dict(model="euler")),
-                          ("generated, SymPy-bodied functors (empty Prims)", dict(bodies=(flux, eig))),
+                          ("generated, SymPy-bodied functors (Prims derived by CSE + strength reduction)", dict(bodies=(flux, eig))),
                           ("generated, user device source, Functions.h signatures (empty Prims)", dict(source=user_source(dim)))):
             k = batched_stateless(KernelBuilder, dim, P, 1, nr, 0)
             if "bodies" in kw:
