@@ -90,7 +90,7 @@ struct Fv2dMarchConfig {
   static_assert(VEC == 32 || VEC == 16 || VEC == (int)sizeof(T), "vector width of the global accesses");
   static_assert(VEC == (int)sizeof(T) || CELL_BYTES % VEC == 0, "a cell must be a whole number of vectors");
 
-  // warp-private exchange area: [COMPS][XS] values; slots [0,32) row buffer 0, [32,64) row buffer 1,
+  // warp-private exchange area: [XVEC][XS] vectors of XPV values + [XREM][XS] values (below); slots [0,32) row buffer 0, [32,64) row buffer 1,
   // [64,96) left face-halo table (patch of the warp, row), [96,128) right face-halo table
   // CellData form: the patches come through per-patch pointers whose alignment the launcher cannot see (the pointer
   // arrays live in device memory).  Each lane looks at ITS patch's pointers and takes the 256-bit access when they
@@ -101,6 +101,16 @@ struct Fv2dMarchConfig {
 #endif
   static constexpr bool DYN_WIDE = EXAHYPE_2D_GATHER_DYN_WIDE && GATHER && VEC == 16 && sizeof(T) == 8 && CELL_BYTES % 32 == 0;
   static constexpr int XS = 128;
+  // The COMPS values a lane publishes are packed into 16-byte vectors, [XVEC][XS] vectors per warp: a neighbour's F_1,
+  // L_1, Q arrive with XVEC 128-bit shared loads instead of COMPS scalar ones (C2: 3 instead of 6 per side and row; a
+  // 64-bit load is two wavefronts per warp plus two more when the edge lane's table entry shares a bank with an
+  // interior reader -- 15 rows of 16 --, a 128-bit load four plus one: 24 -> 15 wavefronts per side and row).
+#ifndef EXAHYPE_2D_XVEC
+#define EXAHYPE_2D_XVEC 1
+#endif
+  static constexpr int XPV = EXAHYPE_2D_XVEC ? 16 / (int)sizeof(T) : 1;       // values per exchange vector
+  static constexpr int XVEC = COMPS / XPV;                                    // whole vectors; the rest stays scalar:
+  static constexpr int XREM = COMPS - XVEC * XPV;                             // [XVEC][XS] vectors, then [XREM][XS] values
   static constexpr int WARP_BYTES = COMPS * XS * (int)sizeof(T);
   static constexpr int SMEM_BYTES = WPC * WARP_BYTES;
   static_assert(SMEM_BYTES <= 227 * 1024, "exchange area does not fit");
@@ -215,6 +225,50 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// One slot of the exchange area: the COMPS values of a cell -- F_1[NR], L_1, Q[DV] -- as XVEC vectors of XPV values
+// ([XVEC][XS] vectors per warp) followed by XREM scalars ([XREM][XS] values)
+template <class C>
+__device__ __forceinline__ void exchange_store(typename C::T* X, int slot, const typename C::T (&v)[C::COMPS]) {
+  using T = typename C::T;
+#pragma unroll
+  for (int w = 0; w < C::XVEC; ++w) {
+    T* p = X + ((long long)w * C::XS + slot) * C::XPV;
+    if constexpr (C::XPV == 1) p[0] = v[w];
+    else if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(p) = make_double2(v[2 * w], v[2 * w + 1]);
+    else *reinterpret_cast<float4*>(p) = make_float4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
+  }
+#pragma unroll
+  for (int c = 0; c < C::XREM; ++c) X[(long long)(C::XVEC * C::XPV + c) * C::XS + slot] = v[C::XVEC * C::XPV + c];
+}
+template <class C>
+__device__ __forceinline__ void exchange_load(const typename C::T* X, int slot, typename C::T (&v)[C::COMPS]) {
+  using T = typename C::T;
+#pragma unroll
+  for (int w = 0; w < C::XVEC; ++w) {
+    const T* p = X + ((long long)w * C::XS + slot) * C::XPV;
+    if constexpr (C::XPV == 1) v[w] = p[0];
+    else if constexpr (sizeof(T) == 8) {
+      const double2 a = *reinterpret_cast<const double2*>(p);
+      v[2 * w] = a.x; v[2 * w + 1] = a.y;
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(p);
+      v[4 * w] = a.x; v[4 * w + 1] = a.y; v[4 * w + 2] = a.z; v[4 * w + 3] = a.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C::XREM; ++c) v[C::XVEC * C::XPV + c] = X[(long long)(C::XVEC * C::XPV + c) * C::XS + slot];
+}
+// what a cell publishes: F_1[NR], L_1, Q[DV]
+template <class C>
+__device__ __forceinline__ void exchange_pack(typename C::T (&v)[C::COMPS], const typename C::T (&f1)[C::NR],
+                                              typename C::T l1, const typename C::T (&q)[C::NV]) {
+#pragma unroll
+  for (int c = 0; c < C::NR; ++c) v[c] = f1[c];
+  v[C::NR] = l1;
+#pragma unroll
+  for (int c = 0; c < C::DV; ++c) v[C::NR + 1 + c] = q[c];
+}
+
 // Per-lane state of the march.  Ring index = row % RING (compile-time in the unrolled loop).
 template <class C>
 struct RowMarch {
@@ -222,7 +276,7 @@ struct RowMarch {
   const T* row_ptr;          // this lane's cell in marching row 0 (haloed i = H-1, j = k+H) of its patch
   const unsigned char* l2_ptr;   // marching row 0, haloed column 0 of the patch (lanes with k == 0 prefetch)
   T* out_ptr;                // this lane's cell in interior row 0 of the output
-  T* X;                      // warp-private exchange area [COMPS][XS]
+  T* X;                      // warp-private exchange area: [XVEC][XS] vectors, [XREM][XS] values
   T dt;
   int lane, k;
   int halo_slot_left, halo_slot_right;   // 64 + sub*P, 96 + sub*P (+ interior row)
@@ -270,8 +324,11 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
     const int rb = (r - 1) & 1;
     const int sl = (m.k == 0) ? (m.halo_slot_left + (r - 2)) : (rb * 32 + m.lane - 1);
     const int sr = (m.k == P - 1) ? (m.halo_slot_right + (r - 2)) : (rb * 32 + m.lane + 1);
-    const T* __restrict__ xl = m.X + sl;
-    const T* __restrict__ xr = m.X + sr;
+    T xl[C::COMPS], xr[C::COMPS];      // the neighbours' F_1[NR], L_1, Q[DV]
+#if !EXAHYPE_2D_WHATIF_NO_EXCHANGE
+    exchange_load<C>(m.X, sl, xl);
+    exchange_load<C>(m.X, sr, xr);
+#endif
     T qc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) qc[v] = q[MID][v];
@@ -282,7 +339,7 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
 #if EXAHYPE_2D_WHATIF_NO_EXCHANGE   // what-if build (WRONG results): how fast would the march be without the lane exchange?
     for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], f0[MID][v], f0[NEW][v]);
 #else
-    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], xr[v * XS], xl[v * XS]);
+    for (int v = 0; v < NR; ++v) qc[v] = Upd::flux(qc[v], xr[v], xl[v]);
 #endif
     // "Q_copy = 0.5*dt*(...) + Q_copy" from the original Q, axis 0 then axis 1 (test.cpp:78-95)
 #pragma unroll
@@ -293,10 +350,10 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
       qc[v] = Upd::dissipation(qc[v], q[MID][v], q[NEW][v], q_old[v], l1_mid, l0[NEW], l0[OLD], m.dt);
 #else
     {
-      const T l_plus = xr[NR * XS], l_minus = xl[NR * XS];
+      const T l_plus = xr[NR], l_minus = xl[NR];
 #pragma unroll
       for (int v = 0; v < DV; ++v)
-        qc[v] = Upd::dissipation(qc[v], q[MID][v], xr[(NR + 1 + v) * XS], xl[(NR + 1 + v) * XS], l1_mid, l_plus, l_minus,
+        qc[v] = Upd::dissipation(qc[v], q[MID][v], xr[NR + 1 + v], xl[NR + 1 + v], l1_mid, l_plus, l_minus,
                                  m.dt);
     }
 #endif
@@ -323,12 +380,9 @@ __device__ __forceinline__ void march_row(const RowMarch<C>& m, int r, typename 
 #endif
   if (inner) {
     // ---------------------------------------------------------------- publish row r for the neighbouring lanes
-    T* __restrict__ xw = m.X + (r & 1) * 32 + m.lane;
-#pragma unroll
-    for (int v = 0; v < NR; ++v) xw[v * XS] = f1[v];
-    xw[NR * XS] = l1_new;
-#pragma unroll
-    for (int v = 0; v < DV; ++v) xw[(NR + 1 + v) * XS] = q[NEW][v];
+    T pub[C::COMPS];
+    exchange_pack<C>(pub, f1, l1_new, q[NEW]);
+    exchange_store<C>(m.X, (r & 1) * 32 + m.lane, pub);
   }
   __syncwarp();
 }
@@ -427,12 +481,9 @@ fv2d_march_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_p
       const auto pr = Phys::template prims<T>(qh);
       T F[NR];
       Phys::template flux<1, T>(qh, pr, F);
-      T* __restrict__ xw = m.X + (side ? 96 : 64) + lane;
-#pragma unroll
-      for (int v = 0; v < NR; ++v) xw[v * XS] = F[v];
-      xw[NR * XS] = Phys::template eigen<1, T>(qh, pr);
-#pragma unroll
-      for (int v = 0; v < DV; ++v) xw[(NR + 1 + v) * XS] = qh[v];
+      T pub[C::COMPS];
+      exchange_pack<C>(pub, F, Phys::template eigen<1, T>(qh, pr), qh);
+      exchange_store<C>(m.X, (side ? 96 : 64) + lane, pub);
     }
     __syncwarp();
   }

@@ -33,7 +33,11 @@ KEEP = re.compile(
 
 
 def report(path, out, key=None):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):      # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): the report itself stayed there
+        with open(path) as f:
+            raw = f.read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, unit = rows[0], rows[1]
     lines = []
