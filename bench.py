@@ -555,7 +555,7 @@ def main():
                              % (q_in.numel() * q_in.element_size() / 1e9, q_out.numel() * q_out.element_size() / 1e9),
                        "kernel": info},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                         "traffic": recorded_traffic(args.workload + ("_unknowns" if args.output == "unknowns" else "")), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                          "kernel_ms_source": ("mean of per-launch CUDA event pairs inside the timed region" if args.step_events else
                                               "timed region / launches (two CUDA events around the K steps; includes launch gaps)"),
