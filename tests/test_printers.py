@@ -174,3 +174,58 @@ def test_generated_3d_unit_instantiates_the_warp_per_patch_template(tmp_path):
         assert hasattr(ctypes.CDLL(built.lib_path), f"step3d_{dtype}")
     with pytest.raises(Exception):
         CUDAPrinter(batched_stateless(KernelBuilder, 3, 4, 1, 5, 0), model="euler", template="pair")
+
+
+def _euler_sympy_bodies(dim, gamma=1.4):
+    import sympy
+
+    def flux(q, n):
+        irho = 1 / q[0]
+        ke = sum(q[1 + a] * q[1 + a] for a in range(dim))
+        p = (gamma - 1) * (q[dim + 1] - sympy.Rational(1, 2) * irho * ke)
+        coeff = irho * q[n + 1]
+        f = [coeff * q[v] for v in range(dim + 1)] + [coeff * q[dim + 1] + coeff * p]
+        f[n + 1] = f[n + 1] + p
+        return f
+
+    def eig(q, n):
+        irho = 1 / sympy.Abs(q[0])
+        ke = sum(q[1 + a] * q[1 + a] for a in range(dim))
+        p = (gamma - 1) * (q[dim + 1] - sympy.Rational(1, 2) * irho * ke)
+        c = sympy.sqrt(gamma * sympy.Abs(p) * irho)
+        u = q[n + 1] * irho
+        return sympy.Max(sympy.Abs(u - c), sympy.Abs(u + c))
+    return flux, eig
+
+
+def test_strength_reduction_of_sympy_functors_keeps_the_values():
+    """CUDAPrinter.strength_reduce gathers a product's half-power factors under one root and turns 1/|x| into |1/x|
+    (opaque functions, so that SymPy does not split them again): same values to rounding, one reciprocal and one root
+    per cell in the generated per-cell cache."""
+    import sympy
+    from exahype_b200.printers.CUDAPrinter import strength_reduce
+    q = sympy.symbols("q0:5", real=True)
+    flux, eig = _euler_sympy_bodies(3)
+    rng = np.random.default_rng(5)
+    states = np.column_stack([rng.uniform(0.5, 2.0, 200) * rng.choice([-1.0, 1.0], 200),     # either sign of the density
+                              rng.uniform(-1, 1, (200, 3)), rng.uniform(2.0, 4.0, 200)])
+    custom = {"exahype_recip": lambda x: 1.0 / x, "exahype_sqrt": np.sqrt}
+    for n in range(3):
+        for expr in list(flux(list(q), n)) + [eig(list(q), n)]:
+            reduced = strength_reduce(expr)
+            f0 = sympy.lambdify(q, expr, "numpy")
+            f1 = sympy.lambdify(q, reduced, [custom, "numpy"])
+            a, b = f0(*states.T) * np.ones(200), f1(*states.T) * np.ones(200)
+            np.testing.assert_allclose(b, a, rtol=2e-13, atol=2e-13)      # a/b against a*(1/b), and cancellation in F
+    # the eigenvalue: SymPy's own form has two roots and a reciprocal of |rho|, the reduced one a single root
+    from sympy.core.function import AppliedUndef
+    roots = {a for a in strength_reduce(eig(list(q), 0)).atoms(AppliedUndef) if a.func.__name__ == "exahype_sqrt"}
+    assert len(roots) == 1 and len(eig(list(q), 0).atoms(sympy.Pow)) > 2
+    k = batched_stateless(KernelBuilder, 3, 8, 1, 5, 0)
+    k.all_items["Flux"].deviceBody(flux)
+    k.all_items["maxEigenvalue"].deviceBody(eig)
+    code = CUDAPrinter(k, function_name="sympy_euler3d").code
+    prims = code[code.index("Prims<T> prims("):code.index("return pr;")]
+    assert prims.count("T(1.0)/(") == 1 and prims.count("fv_sqrt<T>(") == 1, prims
+    body = code[code.index("return pr;"):code.index("using Update")]
+    assert "T(1.0)/(" not in body and "fv_sqrt" not in body       # flux / eigenvalue calls only combine cached values
