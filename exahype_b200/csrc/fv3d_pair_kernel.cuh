@@ -355,6 +355,9 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
   // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
   // behind the __syncwarp instead of at the end of the step (half a step more lead for the TMA).
+#ifndef EXAHYPE_3D_INTERLEAVE
+#define EXAHYPE_3D_INTERLEAVE 1
+#endif
 #ifndef EXAHYPE_3D_EARLY_HALOED
 #define EXAHYPE_3D_EARLY_HALOED 1
 #endif
@@ -505,7 +508,15 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   __syncwarp();
 
   ps.n_warps = (long long)gridDim.x * C::NW;
+  // Patches are dealt to the warps CTA-interleaved (warp w of CTA c is worker w * grid + c): a round that does not fill
+  // the grid -- the last one of a batch, or the only one of a small batch -- then spreads over all SMs with fewer warps
+  // each, instead of filling some SMs and leaving the others idle (C5's small batches; EXAHYPE_3D_INTERLEAVE=0: the
+  // CTA-major order of round 1).
+#if EXAHYPE_3D_INTERLEAVE
+  const long long w_index = (long long)warp * gridDim.x + blockIdx.x;
+#else
   const long long w_index = (long long)blockIdx.x * C::NW + warp;
+#endif
   const long long my_patches = (n_patches > w_index) ? (n_patches - w_index + ps.n_warps - 1) / ps.n_warps : 0;
   ps.n_my_patches = (int)my_patches;
   ps.pi = ps.slot = 0;
@@ -620,7 +631,7 @@ struct Fv3dPairLauncher {
       cached_sms[dev] = sms;
       cached_ctas_per_sm[dev] = per_sm;
     }
-    const long long ctas_needed = (n_patches + C::NW - 1) / C::NW;
+    const long long ctas_needed = EXAHYPE_3D_INTERLEAVE ? n_patches : (n_patches + C::NW - 1) / C::NW;
     const long long resident = (long long)cached_sms[dev] * cached_ctas_per_sm[dev];
     info->grid = (int)(ctas_needed < resident ? ctas_needed : resident);
     info->block = C::NT;
