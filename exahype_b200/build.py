@@ -23,7 +23,9 @@ LIB = os.path.join(HERE, "libexahype_cuda.so")
 SOURCES = ["exahype_cuda.cu", "inst_euler3d.cu", "inst_euler2d.cu", "inst_swe2d.cu", "inst_fast.cu", "synthetic.cu", "peer_reduce.cu"]
 # per-source flags appended after NVCC_FLAGS: the opt-in fast-arithmetic instantiations are the one unit whose
 # multiply-add pairs may contract (every kernel in it carries the ArithFast policy type, csrc/physics.cuh)
-SOURCE_FLAGS = {"inst_fast.cu": ["-fmad=true"]}
+# (EXAHYPE_FAST_FMAD=false in the environment: tuning builds that keep the branch-free reciprocal / root but not the
+# contraction -- what the range checks and slow paths of the IEEE operations cost on their own)
+SOURCE_FLAGS = {"inst_fast.cu": ["-fmad=" + os.environ.get("EXAHYPE_FAST_FMAD", "true")]}
 HEADERS = ["fv_patch_kernel.cuh", "peer_mail.cuh", "fv3d_march_kernel.cuh", "fv3d_pair_kernel.cuh", "fv2d_march_kernel.cuh", "physics.cuh", "fv_registry.h", os.path.join("..", "..", "include", "exahype_cuda.h")]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-lineinfo",

@@ -314,6 +314,45 @@ def test_unknowns_only_output_is_the_unhaloed_one_without_auxiliary_variables(to
     assert_bitwise(got, interior(upd, want), "unknowns == unhaloed")
 
 
+# densities / water heights far from 1 whose every intermediate stays finite, across 600 orders of magnitude: operands
+# for which nvcc's IEEE division / square root leave their fast path (tiny and huge exponents, subnormal reciprocals:
+# 1/5e307, a zero radicand) next to ordinary ones
+HOSTILE_EULER = [1e-100, -1e-100, 1e-140, 3.0e-151, 3.1e-151, 1e100, 3.2e150, 3.3e150, 1e200, 1e300, 5e307, -1e250]
+HOSTILE_SWE = [1e-100, -1e-120, 1e-140, 3.0e-151, 3.1e-151, 1e-152, 1e100, 1e140, 3.2e150, 3.3e150, 1e151]
+
+
+@pytest.mark.parametrize("model,dim,P,nr,na", [("euler", 3, 8, 5, 0), ("euler", 2, 16, 4, 0), ("swe", 2, 32, 3, 1),
+                                               ("euler", 3, 4, 5, 0), ("euler", 2, 3, 4, 0), ("swe_source", 2, 16, 3, 3)])
+@pytest.mark.parametrize("diss", ["var0", "all"])
+def test_extreme_magnitudes_and_zero_pressure_bit_for_bit(torch, rt, oracle, model, dim, P, nr, na, diss):
+    """Bitwise parity away from the benchmark's O(1) states: densities of either sign across 600 orders of magnitude
+    (including reciprocals that are subnormal) and exactly zero pressures (sqrt(0)), one of each per patch, anywhere in
+    the haloed patch.  These are the operands for which the IEEE division / root take their slow paths; any arithmetic
+    policy that is to replace the per-operation IEEE code (the branch-free ArithFast sequences are bit-identical only
+    inside the fast paths' range) has to pass this.  (Inputs that drive the REFERENCE to infinities or
+    NaNs are outside what this checks: the cheaper physics forms of csrc/physics.cuh are identities for finite values.)"""
+    upd = rt.PatchUpdate(model, dim, P, 1, nr, na, dissipation=diss)
+    cfg = oracle_cfg(oracle, upd)
+    n = 3 * upd.launch_info(10 ** 6)["patches_per_tile"] * 3 + 5
+    q0 = oracle.fill_synthetic(cfg, n)
+    rng = np.random.default_rng(3)
+    hostile = HOSTILE_EULER if model == "euler" else HOSTILE_SWE
+    side = P + 2
+    for p_ in range(n):        # ONE hostile density per patch (two of them side by side would overflow the reference
+        a = rng.integers(0, side, dim)                   # itself) and one zero-pressure cell
+        q0[(p_,) + tuple(a) + (0,)] = hostile[p_ % len(hostile)]
+        if model == "euler":
+            b = (a + 1 + rng.integers(0, side - 1, dim)) % side        # differs from a in every index
+            q0[(p_,) + tuple(b) + (slice(1, dim + 2),)] = 0.0          # no momentum, no energy -> p = 0 -> sqrt(0)
+    want = q0.copy()
+    lam_o, lmax_o = oracle.step(cfg, want, 0.01, nthreads=4)
+    assert np.isfinite(want).all() and np.isfinite(lam_o).all(), "the test's states must keep the reference finite"
+    got, lam, lmax = gpu_step(torch, upd, q0, 0.01)
+    assert_bitwise(got, want, "state")
+    assert_bitwise(lam, lam_o, "lambda_patch")
+    assert lmax == float(lmax_o)
+
+
 # ----------------------------------------------------------------------------------------- semantics of the boundary
 def test_out_of_place_haloed_writes_interior_only(torch, rt, oracle):
     upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0)
