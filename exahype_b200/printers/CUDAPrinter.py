@@ -796,6 +796,7 @@ class CUDAPrinter(CodePrinter):
             f"int {fname}(const void* q_in, void* q_out, int64_t n_patches, double dt, void* lambda_patch, void* lambda_max,\n"
             f"    unsigned flags, void* stream) {{\n"
             "  cudaStream_t s = static_cast<cudaStream_t>(stream);\n"
+            "  if (flags & ~6u) return -1;   // a generated unit knows the two output layouts and the accumulate bit, nothing else\n"
             f"  if (lambda_max && !(flags & 4u) && cudaMemsetAsync(lambda_max, 0, sizeof({T}), s) != cudaSuccess) return -3;\n"
             "  if (n_patches <= 0) return n_patches < 0 ? -1 : 0;\n"
             "  if (!q_in || !q_out || ((uintptr_t)q_in & 15) || ((uintptr_t)q_out & 15)) return -1;\n"
@@ -809,7 +810,7 @@ class CUDAPrinter(CodePrinter):
             f'extern "C" __attribute__((visibility("default")))\n'
             f"int {fname}_cell_data(const exahype_cell_data* cells, double dt, void* lambda_max, unsigned flags, void* stream) {{\n"
             "  cudaStream_t s = static_cast<cudaStream_t>(stream);\n"
-            "  if (!cells || cells->n_patches < 0) return -1;\n"
+            "  if (!cells || cells->n_patches < 0 || (flags & ~6u)) return -1;\n"
             f"  if (lambda_max && !(flags & 4u) && cudaMemsetAsync(lambda_max, 0, sizeof({T}), s) != cudaSuccess) return -3;\n"
             "  if (cells->n_patches == 0) return 0;\n"
             "  if (!cells->q_in || !cells->q_out) return -1;\n"
