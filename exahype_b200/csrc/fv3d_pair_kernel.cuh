@@ -195,10 +195,27 @@ struct PairStream {
       // haloed layout: interior rows of the plane are runs of P*NV values (test.cpp:96-104 writes all NV)
       T* dst = out_base + (plane + C::H) * C::PLANE_ELEMS;
       constexpr int ROW = C::P * C::NV;
-      for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
-        const int row = e / ROW;
-        const int sgm = e / C::SEG_ELEMS;
-        dst[((row + C::H) * C::S + C::H) * C::NV + (e - row * ROW)] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+      constexpr int ROW_GAP = C::S * C::NV - ROW;        // the halo cells between two interior rows
+      if constexpr (ROW >= 32 && C::SEG_ELEMS % 32 == 0 && C::OUT_PLANE_ELEMS % 32 == 0) {
+        // Value e = lane + 32 i of the plane: with rows of at least a warp's width and segments of whole warps, its
+        // staging segment is the same for every lane and its row is that of value 32 i or the next one -- every offset
+        // is a compile-time constant but for one compare per store (the general loop below costs two divisions and
+        // a dozen integer instructions per value: a third of the step's instructions in the reference's in-place form).
+        const T* src = sbuf + lane;
+        T* d0 = dst + (C::H * C::S + C::H) * C::NV + lane;
+#pragma unroll
+        for (int i = 0; i < C::OUT_PLANE_ELEMS / 32; ++i) {
+          const int e0 = 32 * i, row0 = e0 / ROW, col0 = e0 % ROW;
+          const int s_off = e0 + (e0 / C::SEG_ELEMS) * (C::SEG_PITCH - C::SEG_ELEMS);
+          const int wrap = (lane + col0 >= ROW) ? ROW_GAP : 0;
+          d0[e0 + row0 * ROW_GAP + wrap] = src[s_off];
+        }
+      } else {
+        for (int e = lane; e < C::OUT_PLANE_ELEMS; e += 32) {
+          const int row = e / ROW;
+          const int sgm = e / C::SEG_ELEMS;
+          dst[((row + C::H) * C::S + C::H) * C::NV + (e - row * ROW)] = sbuf[sgm * C::SEG_PITCH + (e - sgm * C::SEG_ELEMS)];
+        }
       }
     }
   }
@@ -355,6 +372,9 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
   // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
   // behind the __syncwarp instead of at the end of the step (half a step more lead for the TMA).
+#ifndef EXAHYPE_3D_MINB
+#define EXAHYPE_3D_MINB 1                 // CTAs per SM the register allocation aims at (tuning: one-warp CTAs, 9 per SM)
+#endif
 #ifndef EXAHYPE_3D_INTERLEAVE
 #define EXAHYPE_3D_INTERLEAVE 1
 #endif
@@ -473,7 +493,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NT, EXAHYPE_3D_MINB)
 fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
                  typename C::T* __restrict__ lambda_patch, typename C::T* __restrict__ lambda_max,
                  const FvGather<typename C::T> gather) {
