@@ -697,6 +697,30 @@ def time_kernel_only(torch, runtime, wl, output="unhaloed", diss="var0", kern="a
     return {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3), "algorithmic_GBs": gbs}
 
 
+def time_in_place(torch, runtime, wl, diss="var0", steps=10):
+    """The reference's own call shape -- ``time_step(Q, dt)``: haloed, IN PLACE (q_out == q_in) -- kernel only.  The state is
+    restored from a pristine copy before every launch, outside that launch's events (repeated in-place steps would leave
+    the admissible synthetic input)."""
+    model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    upd = runtime.PatchUpdate(model, dim, P, h, nr, na, dtype=dtype, dissipation=diss, output="haloed")
+    q0 = synthetic_on_device(torch, upd, 0, batch, tdt)
+    q = q0.clone()
+    lam = torch.zeros(1, dtype=tdt, device="cuda")
+    ms = 0.0
+    for it in range(3 + steps):
+        q.copy_(q0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        upd.step(q, None, 0.01, None, lam)
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ms += a.elapsed_time(b) / steps
+    gbs = upd.algorithmic_bytes_per_patch * batch / (ms * 1e-3) / 1e9
+    return {"ms": ms, "cell_updates_per_s": batch * P ** dim / (ms * 1e-3), "algorithmic_GBs": gbs}
+
+
 def time_variants(torch, runtime, args):
     """Kernel-only timings of the other committed variants / workloads (informative; same timing hygiene)."""
     res = {}
@@ -707,6 +731,9 @@ def time_variants(torch, runtime, args):
                                    for k in (("auto", "cell") if dim == 3 else ("auto",))]:
             res[f"{wl}/{output}/{diss}" + ("/cell-kernel" if kern == "cell" else "")] = \
                 time_kernel_only(torch, runtime, wl, output, diss, kern)
+        if wl != "c1":
+            for diss in ("var0", "all"):
+                res[f"{wl}/haloed-in-place/{diss} (the reference's call shape)"] = time_in_place(torch, runtime, wl, diss)
     # the CellData form (per-patch pointers + per-patch dt) on the headline workload: same kernel, gathered addressing
     for wl in ("c3", "c2"):
         model, dim, P, h, nr, na, dtype, batch, _ = WORKLOADS[wl]
