@@ -129,6 +129,11 @@ struct PairStream {
   const T* p_src;
   long long p_patch;
   int p_ip, p_slot, p_left;
+  // CellData form: the table entries (QIn, QOut, dt) of this warp's NEXT patch are read one patch ahead, so that the
+  // dependent loads -- pointer first, then the data behind it -- are not waited for when the stream gets there
+  const T* p_src_next;
+  T* out_next;
+  T dt_next;
 
   __device__ __forceinline__ void issue_next_load(const FvGather<T>& gather) {
     if (p_left == 0) return;
@@ -144,8 +149,10 @@ struct PairStream {
     if (++p_ip == C::NPL) {
       p_ip = 0;
       p_patch += n_warps;
-      if (C::GATHER) { if (p_left > 0) p_src = gather.q_in[p_patch]; }
-      else p_src += n_warps * C::PATCH_ELEMS;
+      if (C::GATHER) {
+        p_src = p_src_next;                                                 // valid whenever p_left > 0
+        if (p_left > C::NPL) p_src_next = gather.q_in[p_patch + n_warps];   // the patch after the one just begun
+      } else p_src += n_warps * C::PATCH_ELEMS;
     }
     if (++p_slot == C::R) p_slot = 0;
   }
@@ -154,8 +161,17 @@ struct PairStream {
     if (!first) patch += n_warps;
     constexpr int ELEMS = C::UNHALOED ? C::OUT_PATCH_ELEMS : C::PATCH_ELEMS;
     if (C::GATHER) {
-      out_base = gather.q_out[patch];
-      if (gather.dt != nullptr) dt = gather.dt[patch];    // CellData::dt of this patch
+      if (first) {
+        out_base = gather.q_out[patch];
+        if (gather.dt != nullptr) dt = gather.dt[patch];    // CellData::dt of this patch
+      } else {
+        out_base = out_next;
+        if (gather.dt != nullptr) dt = dt_next;
+      }
+      if (pi + 1 < n_my_patches) {
+        out_next = gather.q_out[patch + n_warps];
+        if (gather.dt != nullptr) dt_next = gather.dt[patch + n_warps];
+      }
     } else if (first) {
       out_base = q_out + patch * ELEMS;
     } else {
@@ -547,6 +563,8 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   ps.p_ip = ps.p_slot = 0;
   ps.p_src = q_in;
   if (my_patches > 0) ps.p_src = gather.template in<C::GATHER>(q_in, w_index, C::PATCH_ELEMS);
+  ps.p_src_next = q_in; ps.out_next = q_out; ps.dt_next = dt;
+  if (C::GATHER && my_patches > 1) ps.p_src_next = gather.q_in[w_index + ps.n_warps];
 
   // lane -> (row pair jp, column k): a half-warp holds the pairs {0, 2} or {1, 3}
   PairLane<C> ln;
