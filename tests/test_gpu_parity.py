@@ -480,6 +480,55 @@ def test_cell_data_form_gathered_patches_and_per_patch_dt(torch, rt, oracle, mod
         assert_bitwise(pool.cpu().numpy()[slots], q0, "QIn untouched")
 
 
+@pytest.mark.parametrize("output,dissipation", [("unhaloed", "var0"), ("haloed", "var0"), ("unhaloed", "all")])
+def test_cell_data_form_several_patches_per_warp(torch, rt, oracle, output, dissipation):
+    """The warp-per-patch kernel in its CellData form with more patches than resident warps (148 SMs x 8): every warp
+    walks through three or four patches and reads the table entries (QIn, QOut, dt) of its next patch one patch ahead.
+    Permuted pointers, per-patch dt, a ragged count; every patch bit for bit the oracle's result for its own dt."""
+    upd = rt.PatchUpdate("euler", 3, 8, 1, 5, 0, output=output, dissipation=dissipation)
+    cfg = oracle_cfg(oracle, upd)
+    n, pool_n = 4096 + 37, 4096 + 37 + 11
+    rng = np.random.default_rng(11)
+    slots = rng.permutation(pool_n)[:n]
+    dt_values = np.array([0.004, 0.01, 0.017])
+    which = rng.integers(0, 3, n)
+    dts = dt_values[which]
+    q0 = oracle.fill_synthetic(cfg, n)
+    pool = torch.full(upd.in_shape(pool_n), -5.0, dtype=torch.float64, device="cuda")
+    pool[torch.from_numpy(slots).cuda()] = torch.from_numpy(q0).cuda()
+    per_in = int(np.prod(upd.in_shape(1))) * 8
+    in_ptrs = torch.from_numpy(pool.data_ptr() + slots.astype(np.int64) * per_in).cuda()
+    if output == "haloed":
+        out_pool, out_ptrs, out_slots = pool, in_ptrs, slots
+    else:
+        out_pool = torch.full(upd.out_shape(pool_n), -7.0, dtype=torch.float64, device="cuda")
+        per_out = int(np.prod(upd.out_shape(1))) * 8
+        out_slots = rng.permutation(pool_n)[:n]
+        out_ptrs = torch.from_numpy(out_pool.data_ptr() + out_slots.astype(np.int64) * per_out).cuda()
+    lam = torch.zeros(n, dtype=torch.float64, device="cuda")
+    lmax = torch.zeros(1, dtype=torch.float64, device="cuda")
+    upd.step_cell_data(in_ptrs, out_ptrs, dt_patch=torch.from_numpy(dts).cuda(), max_eigenvalue=lam, lambda_max=lmax)
+    torch.cuda.synchronize()
+    want = q0.copy()
+    lam_o = np.zeros(n)
+    for g, dt in enumerate(dt_values):                     # the oracle once per distinct dt
+        idx = np.nonzero(which == g)[0]
+        part = np.ascontiguousarray(want[idx])
+        l, _ = oracle.step(cfg, part, float(dt), nthreads=4)
+        want[idx] = part
+        lam_o[idx] = l
+    assert_bitwise(lam.cpu().numpy(), lam_o, "maxEigenvalue")
+    assert float(lmax.item()) == float(lam_o.max())
+    out_np = out_pool.cpu().numpy()
+    if output == "haloed":
+        assert_bitwise(out_np[slots], want, "in-place patches")
+    else:
+        assert_bitwise(out_np[out_slots], interior(upd, want), "QOut patches")
+        assert_bitwise(pool.cpu().numpy()[slots], q0, "QIn untouched")
+    untouched = np.setdiff1d(np.arange(pool_n), out_slots)
+    assert (out_np[untouched] == (-5.0 if output == "haloed" else -7.0)).all()
+
+
 @pytest.mark.parametrize("model,P,nr,na", [("euler", 16, 4, 0), ("swe", 32, 3, 1), ("euler", 8, 4, 0)])
 @pytest.mark.parametrize("output", ["haloed", "unhaloed"])
 def test_cell_data_form_mixed_patch_alignment(torch, rt, oracle, model, P, nr, na, output):
