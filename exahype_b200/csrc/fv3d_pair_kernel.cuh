@@ -388,9 +388,6 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   // With one dissipated variable the neighbours' Q the dissipation needs from plane ip are few: read them now, so that
   // nothing touches the ring slot of plane ip after this point and the next plane of the stream can be requested right
   // behind the __syncwarp instead of at the end of the step (half a step more lead for the TMA).
-#ifndef EXAHYPE_3D_MINB
-#define EXAHYPE_3D_MINB 1                 // CTAs per SM the register allocation aims at (tuning: one-warp CTAs, 9 per SM)
-#endif
 #ifndef EXAHYPE_3D_INTERLEAVE
 #define EXAHYPE_3D_INTERLEAVE 1
 #endif
@@ -508,6 +505,11 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   ps.advance_plane();
 }
 
+// CTAs per SM the register allocation aims at.  Tuning switch: with one-warp CTAs (-DEXAHYPE_3D_NW=1) 9 per SM put three
+// warps on one scheduler, which caps a thread at 168 registers -- measured slower (profiles/r02_s3_one_warp_ctas.txt).
+#ifndef EXAHYPE_3D_MINB
+#define EXAHYPE_3D_MINB 1
+#endif
 template <class C>
 __global__ void __launch_bounds__(C::NT, EXAHYPE_3D_MINB)
 fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_patches, typename C::T dt,
