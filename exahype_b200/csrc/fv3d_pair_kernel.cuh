@@ -296,6 +296,13 @@ struct PairWindow {
   T li[3][2];
   Prims pr[3][2];
   T m0[2];     // max(L_0 of the current plane, L_0 of the one before it): computed as the previous plane's "plus" maximum
+  // Functor families WITHOUT a per-cell cache (generated from the user's device source with the Functions.h signatures:
+  // every Flux / maxEigenvalue call evaluates 1/rho, p, c itself) get all three axes of a plane evaluated when the plane
+  // arrives -- one block of code, so the compiler shares the division and the root between the calls -- and F_1, F_2,
+  // L_1, L_2 wait here for the step that updates the plane.  With a cache the two evaluations a step apart share it instead.
+  static constexpr bool STASH = std::is_empty<Prims>::value;
+  T fjs[STASH ? 3 : 1][2][C::NR], fks[STASH ? 3 : 1][2][C::NR];
+  T ljs[STASH ? 3 : 1][2], lks[STASH ? 3 : 1][2];
 };
 
 // plane `W` of the window <- the plane the stream delivers next: state, primitives, F_0, L_0
@@ -313,6 +320,12 @@ __device__ __forceinline__ void pair_load_plane(PairStream<C>& ps, const PairLan
     w.pr[W][c] = Phys::template prims<T>(w.q[W][c]);
     Phys::template flux<0, T>(w.q[W][c], w.pr[W][c], w.fi[W][c]);
     w.li[W][c] = Phys::template eigen<0, T>(w.q[W][c], w.pr[W][c]);
+    if constexpr (PairWindow<C>::STASH) {
+      Phys::template flux<1, T>(w.q[W][c], w.pr[W][c], w.fjs[W][c]);
+      w.ljs[W][c] = Phys::template eigen<1, T>(w.q[W][c], w.pr[W][c]);
+      Phys::template flux<2, T>(w.q[W][c], w.pr[W][c], w.fks[W][c]);
+      w.lks[W][c] = Phys::template eigen<2, T>(w.q[W][c], w.pr[W][c]);
+    }
   }
 }
 
@@ -354,11 +367,18 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   T fj[2][NR], lj[2], lk[2];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    Phys::template flux<1, T>(w.q[MID][c], w.pr[MID][c], fj[c]);
-    lj[c] = Phys::template eigen<1, T>(w.q[MID][c], w.pr[MID][c]);
     T F[NR];
-    Phys::template flux<2, T>(w.q[MID][c], w.pr[MID][c], F);
-    lk[c] = Phys::template eigen<2, T>(w.q[MID][c], w.pr[MID][c]);
+    if constexpr (PairWindow<C>::STASH) {
+#pragma unroll
+      for (int v = 0; v < NR; ++v) { fj[c][v] = w.fjs[MID][c][v]; F[v] = w.fks[MID][c][v]; }
+      lj[c] = w.ljs[MID][c];
+      lk[c] = w.lks[MID][c];
+    } else {
+      Phys::template flux<1, T>(w.q[MID][c], w.pr[MID][c], fj[c]);
+      lj[c] = Phys::template eigen<1, T>(w.q[MID][c], w.pr[MID][c]);
+      Phys::template flux<2, T>(w.q[MID][c], w.pr[MID][c], F);
+      lk[c] = Phys::template eigen<2, T>(w.q[MID][c], w.pr[MID][c]);
+    }
     pair_scratch_put<C>(ps.Fk, ps.Lk, ln.sk + c * PK, SK, F, lk[c]);
     // the row above (c = 0) / below (c = 1) belongs to another lane: it reads this row's F_1 / L_1 from the scratch
     pair_scratch_put<C>(ps.Fj, ps.Lj, ln.sj + c * PJ, SJ, fj[c], lj[c]);
@@ -602,6 +622,11 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
       for (int v = 0; v < NR; ++v) w.fi[s][c][v] = T(0);
       w.li[s][c] = T(0);
       w.pr[s][c] = {};
+      if constexpr (PairWindow<C>::STASH) {
+#pragma unroll
+        for (int v = 0; v < NR; ++v) w.fjs[s][c][v] = w.fks[s][c][v] = T(0);
+        w.ljs[s][c] = w.lks[s][c] = T(0);
+      }
     }
   T lam_local = T(0), warp_lam = T(0);
 
