@@ -346,6 +346,55 @@ __device__ __forceinline__ void pair_pre_step(PairStream<C>& ps, const FvGather<
   ps.advance_plane();
 }
 
+// The same two planes in ONE block of code (-DEXAHYPE_3D_MERGED_PRE=1): four independent cells per lane instead of two
+// after each other -- the two pre-steps have no update to overlap their division / root chains with.  Measured: no gain
+// (C3 0.3080 -> 0.3098 ms in a burst, 0.3717 -> 0.3719 sustained, profiles/r02_s3_merged_pre_steps.txt): the request for
+// the previous patch's last slot leaves half a pre-step later, which costs what the shorter chains save.  Off.
+#ifndef EXAHYPE_3D_MERGED_PRE
+#define EXAHYPE_3D_MERGED_PRE 0
+#endif
+template <class C>
+__device__ __forceinline__ void pair_pre_steps_merged(PairStream<C>& ps, const FvGather<typename C::T>& gather,
+                                                      const PairLane<C>& ln, PairWindow<C>& w) {
+  using T = typename C::T;
+  using Phys = typename C::Phys;
+  const T* __restrict__ q0s = ps.wait_plane();
+  ps.advance_plane();
+  const T* __restrict__ q1s = ps.wait_plane();
+  ps.advance_plane();
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int v = 0; v < C::NV; ++v) {
+      w.q[0][c][v] = q0s[(ln.cell + c * C::S) * C::NV + v];
+      w.q[1][c][v] = q1s[(ln.cell + c * C::S) * C::NV + v];
+    }
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int W = 0; W < 2; ++W) {
+      w.pr[W][c] = Phys::template prims<T>(w.q[W][c]);
+      Phys::template flux<0, T>(w.q[W][c], w.pr[W][c], w.fi[W][c]);
+      w.li[W][c] = Phys::template eigen<0, T>(w.q[W][c], w.pr[W][c]);
+    }
+  if constexpr (PairWindow<C>::STASH) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      Phys::template flux<1, T>(w.q[1][c], w.pr[1][c], w.fjs[1][c]);
+      w.ljs[1][c] = Phys::template eigen<1, T>(w.q[1][c], w.pr[1][c]);
+      Phys::template flux<2, T>(w.q[1][c], w.pr[1][c], w.fks[1][c]);
+      w.lks[1][c] = Phys::template eigen<2, T>(w.q[1][c], w.pr[1][c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) w.m0[c] = fv_max(w.li[1][c], w.li[0][c]);
+  __syncwarp();
+  // the two slots requested now: the last plane of the previous patch (none before the first patch: the ring was filled
+  // at start-up) and plane 0, both read by every lane before the __syncwarp
+  if (ps.pi >= 1) ps.issue_next_load(gather);
+  ps.issue_next_load(gather);
+}
+
 // Interior plane ip (1..P) of the current patch, window phase PH = ip % 3:
 //   plane ip+1 -> window;  F_1, F_2, L_1, L_2 of plane ip (+ this lane's face column) -> registers / scratch;  __syncwarp;
 //   update plane ip -> staging;  __syncwarp;  drain;  request the next plane of the stream.
@@ -642,8 +691,12 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
   if (ps.n_my_patches > 0) ps.dt = peer_loop_dt<T>(gather.peer, lane, ps.dt, first_warp);
   for (; ps.pi < ps.n_my_patches; ++ps.pi) {
     ps.begin_patch(gather, ps.pi == 0);
+#if EXAHYPE_3D_MERGED_PRE
+    pair_pre_steps_merged<C>(ps, gather, ln, w);
+#else
     pair_pre_step<C, 0>(ps, gather, ln, w);
     pair_pre_step<C, 1>(ps, gather, ln, w);
+#endif
     int ip = 1;
     while (true) {
       pair_main_step<C, 1>(ps, gather, ip, ln, w, lam_local, warp_lam);
