@@ -286,6 +286,13 @@ __device__ __forceinline__ void pair_scratch_get(const typename C::T* F_base, co
   }
 }
 
+#ifndef EXAHYPE_3D_EARLY_HALOED
+#define EXAHYPE_3D_EARLY_HALOED 1
+#endif
+#ifndef EXAHYPE_3D_EARLY2
+#define EXAHYPE_3D_EARLY2 1
+#endif
+
 // the axis-0 window of one lane: three planes x two cells, all indices compile-time
 template <class C>
 struct PairWindow {
@@ -301,12 +308,22 @@ struct PairWindow {
   // arrives -- one block of code, so the compiler shares the division and the root between the calls -- and F_1, F_2,
   // L_1, L_2 wait here for the step that updates the plane.  With a cache the two evaluations a step apart share it instead.
   static constexpr bool STASH = std::is_empty<Prims>::value;
+  // EXAHYPE_3D_EARLY2 (one dissipated variable, dense batch): everything a lane reads from a plane's ring slot -- its two
+  // cells, its face-halo column and the six neighbour values of the dissipation -- is read when the plane ARRIVES and
+  // waits here for the step that updates the plane, so the slot goes back to the TMA a whole step earlier: a fifth plane
+  // in flight per warp without the shared memory of a fifth slot.  254 registers (206 without), no spills; C3 0.3066 ->
+  // 0.3032 ms, 4 096 patches 0.0505 -> 0.0499 (profiles/r02_s3_early_slot_release.txt).  The CellData form and the
+  // cache-less families have no registers left for it (they would spill) and keep releasing the slot a step later; so do
+  // the haloed output form (in place 0.332 -> 0.343 ms with it) and the geometry with two staging buffers that the
+  // fast arithmetic runs (0.293 -> 0.338 ms with it): measured in the same call, same file.
+  static constexpr bool EARLY2 = EXAHYPE_3D_EARLY2 && (C::DV == 1) && C::UNHALOED && (C::SB == 1) && !C::GATHER && !STASH;
+  T fq[EARLY2 ? 3 : 1][C::NV], qn[EARLY2 ? 3 : 1][6];
   T fjs[STASH ? 3 : 1][2][C::NR], fks[STASH ? 3 : 1][2][C::NR];
   T ljs[STASH ? 3 : 1][2], lks[STASH ? 3 : 1][2];
 };
 
 // plane `W` of the window <- the plane the stream delivers next: state, primitives, F_0, L_0
-template <class C, int W>
+template <class C, int W, bool EXTRAS = true>
 __device__ __forceinline__ void pair_load_plane(PairStream<C>& ps, const PairLane<C>& ln, PairWindow<C>& w) {
   using T = typename C::T;
   using Phys = typename C::Phys;
@@ -315,6 +332,18 @@ __device__ __forceinline__ void pair_load_plane(PairStream<C>& ps, const PairLan
   for (int c = 0; c < 2; ++c)
 #pragma unroll
     for (int v = 0; v < C::NV; ++v) w.q[W][c][v] = qs[(ln.cell + c * C::S) * C::NV + v];
+  if constexpr (PairWindow<C>::EARLY2 && EXTRAS) {
+    // (a halo plane arriving as the last plane of a patch is never updated: what is read of it here is not used)
+#pragma unroll
+    for (int v = 0; v < C::NV; ++v) w.fq[W][v] = qs[ln.f_cell * C::NV + v];
+    w.qn[W][0] = qs[(ln.cell - C::S) * C::NV];
+    w.qn[W][1] = qs[(ln.cell + 2 * C::S) * C::NV];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      w.qn[W][2 + 2 * c] = qs[(ln.cell + c * C::S - 1) * C::NV];
+      w.qn[W][3 + 2 * c] = qs[(ln.cell + c * C::S + 1) * C::NV];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     w.pr[W][c] = Phys::template prims<T>(w.q[W][c]);
@@ -333,16 +362,19 @@ __device__ __forceinline__ void pair_load_plane(PairStream<C>& ps, const PairLan
 template <class C, int W>
 __device__ __forceinline__ void pair_pre_step(PairStream<C>& ps, const FvGather<typename C::T>& gather,
                                               const PairLane<C>& ln, PairWindow<C>& w) {
-  pair_load_plane<C, W>(ps, ln, w);
+  pair_load_plane<C, W, W == 1>(ps, ln, w);
   // The slot requested next is that of the previous plane of the stream.  W == 0: the last plane of the previous patch,
   // last read before the closing __syncwarp of the previous step.  W == 1: plane 0, which every lane has read once the
   // warp meets here (halo planes are never read from the ring again).
+  // EARLY2: the slot of the plane just read, once every lane has read it.
   if (W == 1) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) w.m0[c] = fv_max(w.li[1][c], w.li[0][c]);
     __syncwarp();
+  } else if (PairWindow<C>::EARLY2) {
+    __syncwarp();
   }
-  if (W == 1 || ps.pi >= 1) ps.issue_next_load(gather);
+  if (PairWindow<C>::EARLY2 || W == 1 || ps.pi >= 1) ps.issue_next_load(gather);
   ps.advance_plane();
 }
 
@@ -358,6 +390,7 @@ __device__ __forceinline__ void pair_pre_steps_merged(PairStream<C>& ps, const F
                                                       const PairLane<C>& ln, PairWindow<C>& w) {
   using T = typename C::T;
   using Phys = typename C::Phys;
+  static_assert(!PairWindow<C>::EARLY2, "the merged pre-steps keep the one-step-later slot release");
   const T* __restrict__ q0s = ps.wait_plane();
   ps.advance_plane();
   const T* __restrict__ q1s = ps.wait_plane();
@@ -438,7 +471,7 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
   {
     T q[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) q[v] = qm[ln.f_cell * NV + v];
+    for (int v = 0; v < NV; ++v) q[v] = PairWindow<C>::EARLY2 ? w.fq[MID][v] : qm[ln.f_cell * NV + v];
     const auto pr = Phys::template prims<T>(q);
     T F[NR];
     T L;
@@ -460,12 +493,17 @@ __device__ __forceinline__ void pair_main_step(PairStream<C>& ps, const FvGather
 #ifndef EXAHYPE_3D_INTERLEAVE
 #define EXAHYPE_3D_INTERLEAVE 1
 #endif
-#ifndef EXAHYPE_3D_EARLY_HALOED
-#define EXAHYPE_3D_EARLY_HALOED 1
-#endif
   constexpr bool EARLY = (C::DV == 1) && (C::UNHALOED || EXAHYPE_3D_EARLY_HALOED);
   T qn_j[2], qn_k[2][2];   // [cell]: the neighbour across axis 1 outside the pair; [cell][-1 / +1] along axis 2
-  if constexpr (EARLY) {
+  if constexpr (PairWindow<C>::EARLY2) {
+    qn_j[0] = w.qn[MID][0];
+    qn_j[1] = w.qn[MID][1];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      qn_k[c][0] = w.qn[MID][2 + 2 * c];
+      qn_k[c][1] = w.qn[MID][3 + 2 * c];
+    }
+  } else if constexpr (EARLY) {
     qn_j[0] = qm[(ln.cell - S) * NV];
     qn_j[1] = qm[(ln.cell + 2 * S) * NV];
 #pragma unroll
@@ -677,6 +715,15 @@ fv3d_pair_kernel(const typename C::T* q_in, typename C::T* q_out, long long n_pa
         w.ljs[s][c] = w.lks[s][c] = T(0);
       }
     }
+  if constexpr (PairWindow<C>::EARLY2) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+#pragma unroll
+      for (int v = 0; v < C::NV; ++v) w.fq[s][v] = T(0);
+#pragma unroll
+      for (int v = 0; v < 6; ++v) w.qn[s][v] = T(0);
+    }
+  }
   T lam_local = T(0), warp_lam = T(0);
 
   // ... and touch nothing the PREVIOUS launch may still be writing (its output may be this launch's input, its last warp
