@@ -176,6 +176,55 @@ def test_generated_3d_unit_instantiates_the_warp_per_patch_template(tmp_path):
         CUDAPrinter(batched_stateless(KernelBuilder, 3, 4, 1, 5, 0), model="euler", template="pair")
 
 
+def test_warp_per_patch_tuning_switches_keep_compiling(tmp_path):
+    """The A/B switches of csrc/fv3d_pair_kernel.cuh at their NON-default values -- ring slot released a step later
+    (EXAHYPE_3D_EARLY2=0), the two window-filling steps of a patch merged, CTA-major patch order -- and the cache-less
+    functor family (registers carry F_1, F_2, L_1, L_2 for one step) still cross-compile without spills."""
+    import importlib
+    from exahype_b200 import build as B
+    cp = importlib.import_module("exahype_b200.printers.CUDAPrinter")     # the module (CSRC / INCLUDE), not the class
+    k = batched_stateless(KernelBuilder, 3, 8, 1, 5, 0)
+    p = CUDAPrinter(k, model="euler", function_name="step3d_switches")
+    src = tmp_path / "step3d_switches.cu"
+    src.write_text(p.code)
+    cmd = [B.nvcc()] + B.NVCC_FLAGS + B._host_compiler_args() + ["-I", cp.CSRC, "-I", cp.INCLUDE, "-Xptxas", "-v",
+           "-DEXAHYPE_3D_EARLY2=0", "-DEXAHYPE_3D_MERGED_PRE=1", "-DEXAHYPE_3D_INTERLEAVE=0",
+           "-c", str(src), "-o", str(tmp_path / "step3d_switches.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    def spills(log):
+        return [ln for ln in log.splitlines() if "spill stores" in ln and "0 bytes stack frame, 0 bytes spill stores" not in ln]
+    assert not spills(r.stderr), spills(r.stderr)
+
+    # cache-less family: the user's device source with the Functions.h signatures, default switches
+    hdr = tmp_path / "Functions3d.cuh"
+    hdr.write_text("""
+template <class T> __device__ void Flux(const T* Q, int normal, T* F) {
+  const T irho = T(1.0) / Q[0];
+  const T p = (T(1.4) - 1) * (Q[4] - T(0.5) * irho * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]));
+  const T coeff = irho * Q[normal + 1];
+  F[0] = coeff * Q[0]; F[1] = coeff * Q[1]; F[2] = coeff * Q[2]; F[3] = coeff * Q[3]; F[4] = coeff * Q[4] + coeff * p;
+  F[normal + 1] += p;
+}
+template <class T> __device__ T maxEigenvalue(const T* Q, int normal) {
+  const T irho = T(1.0) / fabs(Q[0]);
+  const T p = (T(1.4) - 1) * (Q[4] - T(0.5) * irho * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]));
+  const T c = sqrt(T(1.4) * fabs(p) * irho);
+  const T u = Q[normal + 1] * irho;
+  return fmax(fabs(u - c), fabs(u + c));
+}
+""")
+    pu = CUDAPrinter(batched_stateless(KernelBuilder, 3, 8, 1, 5, 0), function_name="user_step3d_stash")
+    assert pu.template == "pair"
+    usrc = tmp_path / "user_step3d_stash.cu"
+    pu.file(str(usrc), header_file_name="Functions3d.cuh")
+    cmd = [B.nvcc()] + B.NVCC_FLAGS + B._host_compiler_args() + ["-I", cp.CSRC, "-I", cp.INCLUDE, "-I", str(tmp_path),
+           "-Xptxas", "-v", "-c", str(usrc), "-o", str(tmp_path / "user_step3d_stash.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not spills(r.stderr), spills(r.stderr)
+
+
 def _euler_sympy_bodies(dim, gamma=1.4):
     import sympy
 
